@@ -1,0 +1,190 @@
+// stage34_generic.cu -- generic (any dim % 8 == 0, any T, nbits 1..8, any doclen) fused
+// residual decompression + MaxSim in plain fp32 on CUDA cores.  It is (a) the scoring path for
+// shapes the tcgen05 kernel does not cover (and for passages too long for its shared-memory
+// tile), (b) the exact-fp32 stage-3+4 hook `cb_score_pids`, and (c) the on-device fp32 yardstick
+// the tensor-core kernel is checked against.  It is NOT a CPU fallback -- it is a CUDA kernel.
+//
+// Restates, per (query q, candidate passage p) pair, without materialising anything:
+//   `_collect_compressed_embs_for_pids` (src/search/ranking.jl:46-67)   -> reads codes/residuals in place
+//   `decompress`  (src/indexing/codecs/residual.jl:759-784)               -> v = C[:,code] + w[bucket]; v ./= (|v| + eps)
+//   `maxsim`      (src/search/ranking.jl:69-86)                           -> sum_t max_e Q[:,t] . v_e
+// Passage-major: a CTA decompresses one passage into shared memory once and scores it against
+// every query of the chunk that holds it as a candidate (bitmap row), so decompression is
+// amortised over the query batch.
+#include "common.cuh"
+
+constexpr int G_THREADS = 256;
+constexpr int G_QB = 32;  // candidate queries whose per-token maxima are kept in smem at once
+
+struct GenericParams {
+  const float* centroids; const float* weights; const int32_t* codes; const uint8_t* residuals;
+  const int64_t* offsets; int dim, nbits, R, T, nq, W, TC;
+  const float* Q;                 // [nq][T][dim]
+  const uint32_t* bitmap;         // [Np][W] or nullptr (all nq queries are candidates of every item)
+  const int32_t* pid_list;        // items to process, or nullptr (items = 0..n_items-1)
+  int64_t n_items;
+  unsigned long long* work;       // dynamic work counter
+  const int64_t* list_off; int32_t* cursors; uint64_t* pairs;  // pair-list output (bitmap mode)
+  float* out_scores;              // [n_items][nq] direct output (hook mode) or nullptr
+};
+
+__global__ void __launch_bounds__(G_THREADS)
+k_maxsim_generic(GenericParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int dim = P.dim, T = P.T, ld = dim + 1;
+  float* Ds = reinterpret_cast<float*>(smem_raw);                  // [TC][ld]
+  float* Qs = Ds + (size_t)P.TC * ld;                              // [T][ld]
+  uint32_t* tokmax = reinterpret_cast<uint32_t*>(Qs + (size_t)T * ld);  // [G_QB][T]
+  int* s_q = reinterpret_cast<int*>(tokmax + G_QB * T);            // [CB_NQ_CHUNK]
+  float* s_w = reinterpret_cast<float*>(s_q + CB_NQ_CHUNK);        // [256]
+  __shared__ long long s_item;
+  __shared__ int s_ncand;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = G_THREADS / 32;
+  for (int i = tid; i < (1 << P.nbits); i += G_THREADS) s_w[i] = P.weights[i];
+  const float eps = 1.1920929e-07f;  // eps(Float32)
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_item = (long long)atomicAdd(P.work, 1ULL);
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= P.n_items) break;
+    const int64_t p = P.pid_list ? (int64_t)P.pid_list[item] : (int64_t)item;
+    const int64_t e0 = P.offsets[p];
+    const int L = (int)(P.offsets[p + 1] - e0);
+
+    // candidate queries of this passage
+    if (P.bitmap) {
+      if (warp == 0) {
+        uint32_t w = lane < P.W ? P.bitmap[p * P.W + lane] : 0u;
+        int c = __popc(w), pre = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+        int base = pre - c;
+        while (w) { int b = __ffs(w) - 1; w &= w - 1; s_q[base++] = lane * 32 + b; }
+        if (lane == 31) s_ncand = pre;
+      }
+    } else {
+      for (int i = tid; i < P.nq; i += G_THREADS) s_q[i] = i;
+      if (tid == 0) s_ncand = P.nq;
+    }
+    __syncthreads();
+    const int ncand = s_ncand;
+    if (ncand == 0) continue;
+    if (L == 0) {
+      // a zero-length passage can only appear through an explicit pid list: sum over an empty
+      // max is undefined in the reference (maximum of an empty slice throws); report -inf.
+      if (P.out_scores) for (int i = tid; i < ncand; i += G_THREADS) P.out_scores[item * P.nq + s_q[i]] = -INFINITY;
+      continue;
+    }
+    const int nchunks = (L + P.TC - 1) / P.TC;
+
+    for (int qb = 0; qb < ncand; qb += G_QB) {
+      const int nqb = min(G_QB, ncand - qb);
+      for (int i = tid; i < nqb * T; i += G_THREADS) tokmax[i] = 0u;
+      for (int ch = 0; ch < nchunks; ch++) {
+        const int c0 = ch * P.TC, n = min(P.TC, L - c0);
+        if (!(nchunks == 1 && qb > 0)) {
+          __syncthreads();
+          // ---- stage 3: decompress tokens [c0, c0+n) of the passage: one warp per token
+          for (int e = warp; e < n; e += nwarps) {
+            const int64_t g = e0 + c0 + e;
+            const float* __restrict__ cptr = P.centroids + (int64_t)P.codes[g] * dim;
+            const uint8_t* __restrict__ emb = P.residuals + g * P.R;
+            float ss = 0.f;
+            for (int d = lane; d < dim; d += 32) {
+              float v = __fadd_rn(cptr[d], s_w[cb_bucket_of(emb, d, P.nbits)]);
+              Ds[e * ld + d] = v;
+              ss = fmaf(v, v, ss);
+            }
+            ss = cb_warp_sum(ss);
+            const float denom = __fadd_rn(sqrtf(ss), eps);
+            for (int d = lane; d < dim; d += 32) Ds[e * ld + d] = __fdiv_rn(Ds[e * ld + d], denom);
+          }
+        }
+        // ---- stage 4: every candidate query of the block against the resident tokens
+        for (int qi = 0; qi < nqb; qi++) {
+          __syncthreads();
+          const float* __restrict__ qg = P.Q + (int64_t)s_q[qb + qi] * T * dim;
+          for (int i = tid; i < T * dim; i += G_THREADS) Qs[(i / dim) * ld + (i % dim)] = qg[i];
+          __syncthreads();
+          for (int idx = tid; idx < T * n; idx += G_THREADS) {
+            const int t = idx % T, e = idx / T;
+            const float* a = Qs + t * ld;
+            const float* b = Ds + e * ld;
+            float acc = 0.f;
+            for (int k = 0; k < dim; k++) acc = fmaf(a[k], b[k], acc);
+            atomicMax(&tokmax[qi * T + t], cb_orderable(acc));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- sum over query tokens (fixed order) and emit
+      for (int qi = tid; qi < nqb; qi += G_THREADS) {
+        float s = 0.f;
+        for (int t = 0; t < T; t++) s = __fadd_rn(s, cb_unorderable(tokmax[qi * T + t]));
+        const int q = s_q[qb + qi];
+        if (P.out_scores) {
+          P.out_scores[item * P.nq + q] = s;
+        } else {
+          const int slot = atomicAdd(&P.cursors[q], 1);
+          P.pairs[P.list_off[q] + slot] = cb_pair_key(s, (uint32_t)p);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static int32_t launch_generic(cb_index* ix, GenericParams& P, int64_t max_len, cudaStream_t st) {
+  const int ld = ix->dim + 1;
+  const size_t fixed = ((size_t)P.T * ld + (size_t)G_QB * P.T + CB_NQ_CHUNK + 256) * 4;
+  const size_t budget = 200 * 1024;
+  CB_REQUIRE(fixed + (size_t)ld * 4 <= budget, CB_ERR_UNSUPPORTED,
+             "dim = %d, query length = %d do not fit the generic scoring kernel's shared memory", ix->dim, P.T);
+  int64_t tc = (int64_t)((budget - fixed) / ((size_t)ld * 4));
+  if (max_len < 1) max_len = 1;
+  if (tc > max_len) tc = max_len;
+  P.TC = (int)tc;
+  const size_t smem = fixed + (size_t)P.TC * ld * 4;
+  CB_CUDA(cudaFuncSetAttribute(k_maxsim_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_maxsim_generic, G_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)ix->sm_count * per_sm;
+  if (grid > P.n_items) grid = P.n_items;
+  if (grid < 1) return CB_OK;
+  CB_TRY(ix->misc.ensure(64));
+  P.work = ix->misc.as<unsigned long long>() + 1;
+  CB_CUDA(cudaMemsetAsync(P.work, 0, sizeof(unsigned long long), st));
+  k_maxsim_generic<<<(unsigned)grid, G_THREADS, smem, st>>>(P);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+static void fill_index_params(const cb_index* ix, GenericParams& P) {
+  P.centroids = ix->centroids; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;
+  P.offsets = ix->offsets; P.dim = ix->dim; P.nbits = ix->nbits; P.R = ix->R;
+}
+
+int32_t cb_stage34_generic(cb_index* ix, const float* dQ, int nq, int T, int W, const uint32_t* d_bitmap,
+                           const int32_t* d_pid_list, int64_t n_list, const int64_t* d_list_off,
+                           int32_t* d_cursors, uint64_t* d_pairs, cudaStream_t st) {
+  GenericParams P{};
+  fill_index_params(ix, P);
+  P.T = T; P.nq = nq; P.W = W; P.Q = dQ; P.bitmap = d_bitmap; P.pid_list = d_pid_list;
+  P.n_items = d_pid_list ? n_list : ix->Np;
+  P.list_off = d_list_off; P.cursors = d_cursors; P.pairs = d_pairs; P.out_scores = nullptr;
+  return launch_generic(ix, P, ix->max_doclen, st);
+}
+
+// hook: scores of an explicit (0-based, local) pid list for nq queries, no bitmap.
+int32_t cb_generic_score_list(cb_index* ix, const float* dQ, int nq, int T, const int32_t* d_pid_list,
+                              int64_t n_list, float* d_out_scores, cudaStream_t st) {
+  GenericParams P{};
+  fill_index_params(ix, P);
+  P.T = T; P.nq = nq; P.W = 0; P.Q = dQ; P.bitmap = nullptr; P.pid_list = d_pid_list; P.n_items = n_list;
+  P.out_scores = d_out_scores;
+  return launch_generic(ix, P, ix->max_doclen, st);
+}
