@@ -110,6 +110,7 @@ struct cb_index {
   int32_t* ivf_pids = nullptr;       // [Ne]   local 0-based pid of every IVF entry
   size_t resident_bytes = 0;
   int64_t max_doclen = 0;
+  int32_t n_long = -1, long_limit = 0;  // passages too long for the tcgen05 tile (cached list)
 
   // workspace (grow-only)
   DevBuf q_f32, q_prep, topr_val, topr_idx, cells, cell_scores, flags, bitmap, counts, list_off,

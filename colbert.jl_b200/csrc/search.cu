@@ -6,14 +6,6 @@
 int32_t cb_generic_score_list(cb_index* ix, const float* dQ, int nq, int T, const int32_t* d_pid_list,
                               int64_t n_list, float* d_out_scores, cudaStream_t st);  // stage34_generic.cu
 
-// Passages the tensor-core kernel cannot hold (doclen above its shared-memory tile): collected so
-// the generic kernel scores just those.
-__global__ void k_collect_long(const int64_t* __restrict__ offsets, int64_t Np, int64_t limit,
-                               int32_t* __restrict__ out /* [0] = count, [1..] pids */) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < Np && offsets[p + 1] - offsets[p] > limit) out[1 + atomicAdd(&out[0], 1)] = (int32_t)p;
-}
-
 static int32_t check_query_args(const cb_index* ix, const void* Q, int nq, int T, int nprobe) {
   CB_REQUIRE(ix != nullptr, CB_ERR_BAD_ARG, "index handle is NULL");
   CB_REQUIRE(nq >= 0 && T >= 1, CB_ERR_BAD_ARG, "bad query shape (nq = %d, T = %d)", nq, T);
