@@ -191,6 +191,21 @@ def _collect_compressed_embs_for_pids(doclens, codes, residuals, pids):
     return codes_packed, residuals_packed
 
 
+def _collect_compressed_embs_for_pids_fast(doclens, codes, residuals, pids, pid_offsets=None):
+    """Vectorised twin of `_collect_compressed_embs_for_pids` (same outputs; one fancy-index
+    gather instead of a per-pid loop) used when timing the CPU baseline, so that the Python loop
+    overhead -- which Julia does not pay -- is not billed to the reference."""
+    doclens = np.asarray(doclens, dtype=np.int64)
+    pids = np.asarray(pids, dtype=np.int64)
+    if pid_offsets is None:
+        pid_offsets = _offsets_1based(doclens)
+    sel = doclens[pids - 1] if len(pids) else np.zeros(0, np.int64)
+    total = int(sel.sum())
+    starts = np.repeat(pid_offsets[pids - 1] - 1 - (_offsets_1based(sel) - 1), sel)
+    idx = starts + np.arange(total, dtype=np.int64)
+    return codes[idx], np.asfortranarray(residuals[:, idx])
+
+
 def maxsim(Q, D, pids, doclens):
     """src/search/ranking.jl:69-86 -- score[p] = sum_t max_{e in p} Q[:,t].D[:,e].
     Q (dim, T), D (dim, M) with M = sum(doclens[pids])."""
@@ -297,6 +312,20 @@ def unpack_bucket_indices(dim, nbits, binary_residuals):
     return _unbinarize(_unpackbits(binary_residuals, nbits))
 
 
+def unpack_bucket_indices_fast(dim, nbits, binary_residuals):
+    """Closed form of `unpack_bucket_indices` for nbits in {1, 2, 4, 8} (dimensions never
+    straddle bytes): idx(d) = (byte[(d*nbits) >> 3] >> ((d*nbits) & 7)) & (2^nbits - 1).
+    Pinned equal to the generic bit-stream path by tests/test_oracle_golden.py.  Returns uint8."""
+    assert nbits in (1, 2, 4, 8)
+    per = 8 // nbits
+    b = np.asarray(binary_residuals, dtype=np.uint8)
+    out = np.empty((dim, b.shape[1]), dtype=np.uint8)
+    mask = np.uint8((1 << nbits) - 1)
+    for j in range(per):
+        out[j::per, :] = (b >> np.uint8(j * nbits)) & mask
+    return out
+
+
 def decompress_residuals(dim, nbits, bucket_weights, binary_residuals):
     """src/indexing/codecs/residual.jl:698-721."""
     binary_residuals = np.asarray(binary_residuals, dtype=np.uint8)
@@ -314,7 +343,7 @@ def decompress_residuals(dim, nbits, bucket_weights, binary_residuals):
 
 
 def decompress(dim, nbits, centroids, bucket_weights, codes, residuals, bsize=10000,
-               return_unnormalized=False):
+               return_unnormalized=False, fast=False):
     """src/indexing/codecs/residual.jl:759-784 -- v = centroids[:, code] + w[bucket];
     v ./= (||v||_2 + eps).  Returns Float32 (dim, M)."""
     codes = np.asarray(codes)
@@ -330,7 +359,10 @@ def decompress(dim, nbits, centroids, bucket_weights, codes, residuals, bsize=10
     for o in range(0, len(codes), bsize):
         e = min(len(codes), o + bsize)
         bc = codes[o:e].astype(np.int64) - 1
-        res = decompress_residuals(dim, nbits, bucket_weights, residuals[:, o:e])
+        if fast and nbits in (1, 2, 4, 8):
+            res = np.asarray(bucket_weights, dtype=F32)[unpack_bucket_indices_fast(dim, nbits, residuals[:, o:e])]
+        else:
+            res = decompress_residuals(dim, nbits, bucket_weights, residuals[:, o:e])
         batch = (centroids[:, bc] + res).astype(F32)
         if raw is not None:
             raw[:, o:e] = batch
@@ -407,10 +439,14 @@ def search_all_scores(index: Index, Q, fast=True):
     """src/searching.jl:103-122 for one query matrix Q (dim, T): returns
     (pids ascending, scores in pid order)."""
     pids = retrieve(index.ivf, index.ivf_lengths, index.centroids, index.emb2pid, index.nprobe, Q)
-    codes_packed, residuals_packed = _collect_compressed_embs_for_pids(
-        index.doclens, index.codes, index.residuals, pids)
+    if fast:
+        codes_packed, residuals_packed = _collect_compressed_embs_for_pids_fast(
+            index.doclens, index.codes, index.residuals, pids)
+    else:
+        codes_packed, residuals_packed = _collect_compressed_embs_for_pids(
+            index.doclens, index.codes, index.residuals, pids)
     D = decompress(index.dim, index.nbits, index.centroids, index.bucket_weights,
-                   codes_packed, residuals_packed)
+                   codes_packed, residuals_packed, fast=fast)
     if fast and len(pids) and index.doclens[pids - 1].min() >= 1:
         scores = maxsim_fast(Q, D, pids, index.doclens)
     else:

@@ -94,6 +94,8 @@ def test_collect_compressed_embs_shapes():  # test/search/ranking.jl:123-134
     c, r = O._collect_compressed_embs_for_pids(doclens, codes, residuals, pids)
     assert len(c) == doclens[pids - 1].sum() and r.shape == (16, doclens[pids - 1].sum())
     assert c.dtype == np.uint32 and r.dtype == np.uint8
+    cf, rf = O._collect_compressed_embs_for_pids_fast(doclens, codes, residuals, pids)
+    assert np.array_equal(cf, c) and np.array_equal(rf, r)
 
 
 def test_maxsim_golden():  # test/search/ranking.jl:137-152  (tested with == upstream)
@@ -285,6 +287,15 @@ def test_nbits2_layout_closed_form():  # SURVEY 8a "Resulting bit layout"
     packed1 = rng.integers(0, 256, (16, 50), dtype=np.uint8)
     idx1 = O.unpack_bucket_indices(dim, 1, packed1)
     assert np.array_equal(idx1, (packed1[d >> 3, :] >> (d & 7)[:, None]) & 1)
+    for nb, pk, want in ((1, packed1, idx1), (2, packed, idx), (4, packed4, idx4)):
+        assert np.array_equal(O.unpack_bucket_indices_fast(dim, nb, pk), want)
+    cen = O._normalize_array(rng.standard_normal((dim, 9)).astype(np.float32))
+    codes = rng.integers(1, 10, 50).astype(np.uint32)
+    w = np.linspace(-0.04, 0.04, 4).astype(np.float32)
+    a, ra = O.decompress(dim, 2, cen, w, codes, packed, fast=True, return_unnormalized=True)
+    b, rb = O.decompress(dim, 2, cen, w, codes, packed, fast=False, return_unnormalized=True)
+    assert np.array_equal(ra, rb)                       # c + w[b]: identical
+    np.testing.assert_allclose(a, b, rtol=1e-6)         # norm summation order may differ by an ulp
 
 
 def test_decompress_shapes():  # test/indexing/codecs/residual.jl:993-1007
