@@ -33,16 +33,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hang.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// `backoff_ns` > 0 makes a waiting warp sleep between polls so that roles with slack (e.g. the
+// decompression warps) do not steal issue slots from the warps on the critical path.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, unsigned backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (backoff_ns) __nanosleep(backoff_ns);
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("colbert_b200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
              threadIdx.x, parity);
       __trap();
     }
   }
+}
+
+// One lane of a converged warp.  ptxas knows an elect.sync predicate selects a single lane, so
+// instructions that need warp-uniform operands (UTCHMMA, UBLKCP, UTCBAR) are emitted without the
+// per-lane "waterfall" loops a `lane == 0` test would cost.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
@@ -55,6 +71,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- tcgen05 ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -110,16 +128,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+// ---- register reallocation between warp roles (whole warpgroup, all 4 warps) ----
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- descriptors -----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand in the canonical SWIZZLE_128B layout:
 // rows of 128 bytes (64 x 16-bit along K), 8-row groups 1024 bytes apart (SBO), 16-byte chunk c
 // of row r stored at chunk (c ^ (r & 7)).  Tile base must be 1024-byte aligned; stepping K by
 // 16 elements advances the start address by 32 bytes.
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);  // start address, bits [0,14)
   d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major), bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;         // stride byte offset between 8-row groups, bits [32,46)
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell), bits [46,48)
   d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B, bits [61,64)
   return d;
