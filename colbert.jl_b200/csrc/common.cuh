@@ -102,6 +102,8 @@ struct cb_index {
   // resident index (device)
   float* centroids = nullptr;        // [K][dim] fp32 (exact paths)
   __half* centroids_h = nullptr;     // [K][dim] fp16 (fused fast path gather)
+  uint8_t* centroids_img = nullptr;  // fp16 row image (swizzled MMA operand tiles) for the tcgen05 stage 1; dim = 128 only
+  float centroid_norm_max = 1.f;     // max |centroid| (scales the fp16 rounding guard of stage 1)
   float* weights = nullptr;          // [2^nbits]
   int32_t* codes = nullptr;          // [Ne] 0-based
   uint8_t* residuals = nullptr;      // [Ne][R]
@@ -116,6 +118,8 @@ struct cb_index {
   DevBuf q_f32, q_prep, topr_val, topr_idx, cells, cell_scores, flags, bitmap, counts, list_off,
       cursors, pairs, out_pids, out_scores, out_counts, misc, long_list, hook_a, hook_b, hook_c;
   int64_t* pinned_total = nullptr;  // pinned host scalar(s) for the one D2H per batch
+  const float* q_prep_src = nullptr; // q_prep currently holds the row image of these query tokens ...
+  int64_t q_prep_rows = 0;           // ... (this many rows); reset at the start of every search chunk
 
   // options
   int opt_force_generic = 0;
@@ -124,7 +128,7 @@ struct cb_index {
 
   // stats of the last search
   long long st_launches = 0;
-  double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0;
+  double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0, st_s1_tc_rows = 0;
   double st_ms[5] = {0, 0, 0, 0, 0};  // stage1, stage2, stage34, stage5, total
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -157,6 +161,9 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W,
                       const uint32_t* d_bitmap, const int64_t* d_list_off, int32_t* d_cursors,
                       uint64_t* d_pairs, cudaStream_t st);
 bool cb_stage34_tc_supported(const cb_index* ix, int T);
+// fp32 rows [nrows][128] -> fp16 "row image" [nrows_pad/8][2 K-blocks][8 rows][128 B] (SWIZZLE_128B
+// K-major, 2048 B between 8-row groups): the shared-memory operand layout of both tcgen05 kernels.
+int32_t cb_tc_prep_rows(const float* dX, int64_t nrows, int64_t nrows_pad, uint8_t* d_out, cudaStream_t st);
 
 // Stage 5: first k of each query's list by key descending -> 1-based global pids / scores.
 int32_t cb_stage5_topk(const uint64_t* d_pairs, const int64_t* d_list_off, int nq, int k,

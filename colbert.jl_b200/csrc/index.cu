@@ -40,6 +40,21 @@ __global__ void k_f32_to_f16(const float* __restrict__ in, __half* __restrict__ 
   for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
 }
 
+// max over rows of the L2 norm (one warp per row; non-negative floats order like their bit patterns)
+__global__ void k_max_row_norm(const float* __restrict__ X, int64_t nrows, int dim, unsigned int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float m = 0.f;
+  for (; row < nrows; row += stride) {
+    float ss = 0.f;
+    for (int d = lane; d < dim; d += 32) { const float v = X[row * dim + d]; ss = fmaf(v, v, ss); }
+    ss = cb_warp_sum(ss);
+    m = fmaxf(m, sqrtf(ss));
+  }
+  if (lane == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 // codes: 1-based UInt32 -> 0-based int32 in place; flags any code outside 1:K (residual.jl:766).
 __global__ void k_codes_zero_based(int32_t* __restrict__ codes, int64_t n, int64_t K, int* __restrict__ bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +158,7 @@ static int32_t upload(void* dst, const void* src, size_t bytes, int flags) {
 static void destroy_index(cb_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
-  cudaFree(ix->centroids); cudaFree(ix->centroids_h); cudaFree(ix->weights); cudaFree(ix->codes);
+  cudaFree(ix->centroids); cudaFree(ix->centroids_h); cudaFree(ix->centroids_img); cudaFree(ix->weights); cudaFree(ix->codes);
   cudaFree(ix->residuals); cudaFree(ix->offsets); cudaFree(ix->cell_offsets); cudaFree(ix->ivf_pids);
   DevBuf* bufs[] = {&ix->q_f32, &ix->q_prep, &ix->topr_val, &ix->topr_idx, &ix->cells, &ix->cell_scores,
                     &ix->flags, &ix->bitmap, &ix->counts, &ix->list_off, &ix->cursors, &ix->pairs,
@@ -184,6 +199,20 @@ static int32_t create_impl(cb_index* ix, const float* centroids, const float* bu
   CB_TRY(upload(ix->weights, bucket_weights, sizeof(float) * (1u << ix->nbits), flags));
   k_f32_to_f16<<<grid_for(K * dim), 256>>>(ix->centroids, ix->centroids_h, K * dim);
   CB_LAUNCH_CHECK();
+  {  // largest centroid norm; (dim = 128) the swizzled fp16 operand image of the tcgen05 stage 1
+    CB_CUDA(cudaMemset(d_max, 0, sizeof(unsigned long long)));
+    k_max_row_norm<<<grid_for(K * 32), 256>>>(ix->centroids, K, dim, reinterpret_cast<unsigned int*>(d_max));
+    CB_LAUNCH_CHECK();
+    unsigned int bits = 0;
+    CB_CUDA(cudaMemcpy(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemset(d_max, 0, sizeof(unsigned long long)));
+    memcpy(&ix->centroid_norm_max, &bits, sizeof(float));
+    if (dim == 128) {
+      const int64_t Kpad = (K + 127) / 128 * 128;
+      CB_DEVALLOC(ix->centroids_img, (size_t)Kpad * 256);
+      CB_TRY(cb_tc_prep_rows(ix->centroids, K, Kpad, ix->centroids_img, nullptr));
+    }
+  }
 
   // compressed embeddings
   CB_DEVALLOC(ix->codes, sizeof(int32_t) * Ne);
@@ -347,6 +376,7 @@ extern "C" int32_t cb_get_stat(const cb_index* ix, const char* key, double* valu
   else if (!strcmp(key, "flagged_rows")) *value = ix->st_flagged;
   else if (!strcmp(key, "tc_pairs")) *value = ix->st_tc_pairs;
   else if (!strcmp(key, "generic_pairs")) *value = ix->st_generic_pairs;
+  else if (!strcmp(key, "stage1_tc_rows")) *value = ix->st_s1_tc_rows;
   else if (!strcmp(key, "ms_stage1")) *value = ix->st_ms[0];
   else if (!strcmp(key, "ms_stage2")) *value = ix->st_ms[1];
   else if (!strcmp(key, "ms_stage34")) *value = ix->st_ms[2];

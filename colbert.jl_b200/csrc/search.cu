@@ -27,6 +27,7 @@ static int32_t candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, in
   CB_TRY(ix->cursors.ensure(sizeof(int32_t) * CB_NQ_CHUNK));
   CB_TRY(ix->list_off.ensure(sizeof(int64_t) * (CB_NQ_CHUNK + 1)));
   if (ix->opt_profile) CB_CUDA(cudaEventRecord(ix->ev[0], st));
+  ix->q_prep_src = nullptr;
   CB_TRY(cb_stage1_probe(ix, dQ, nrows, nprobe, ix->cells.as<int32_t>(), ix->cell_scores.as<float>(), st));
   if (ix->opt_profile) CB_CUDA(cudaEventRecord(ix->ev[1], st));
   CB_CUDA(cudaMemsetAsync(ix->bitmap.p, 0, sizeof(uint32_t) * (size_t)ix->Np * W, st));
@@ -60,7 +61,7 @@ int32_t cb_stage34_score(cb_index* ix, const float* dQ, int nq, int T, int W, co
 }
 
 static void reset_stats(cb_index* ix) {
-  ix->st_pairs = ix->st_pair_embs = ix->st_flagged = ix->st_tc_pairs = ix->st_generic_pairs = 0;
+  ix->st_pairs = ix->st_pair_embs = ix->st_flagged = ix->st_tc_pairs = ix->st_generic_pairs = ix->st_s1_tc_rows = 0;
   for (double& m : ix->st_ms) m = 0;
 }
 

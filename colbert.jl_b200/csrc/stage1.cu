@@ -121,7 +121,7 @@ __device__ __forceinline__ bool s1_better(float sa, int32_t ia, float sb, int32_
 __global__ void __launch_bounds__(128)
 k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __restrict__ C, int dim, int nsplit,
                  const float* __restrict__ topv, const int32_t* __restrict__ topi, int nprobe, float guard,
-                 int32_t* __restrict__ cells, float* __restrict__ cell_scores, int32_t* __restrict__ flags) {
+                 float guard_rel, int32_t* __restrict__ cells, float* __restrict__ cell_scores, int32_t* __restrict__ flags) {
   int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -148,6 +148,11 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) excluded = fmaxf(excluded, __shfl_xor_sync(0xffffffffu, excluded, o));
 
+  if (guard_rel > 0.f) {  // tensor-core shortlist: the rounding bound scales with |q|
+    float ss = 0.f;
+    for (int k = lane; k < dim; k += 32) ss = fmaf(q[k], q[k], ss);
+    guard += guard_rel * sqrtf(cb_warp_sum(ss));
+  }
   float last = INFINITY;
   for (int p = 0; p < nprobe; p++) {
     // lane-local best
@@ -236,7 +241,7 @@ __global__ void k_compact_flags(const int32_t* __restrict__ flags, int64_t nrows
 }
 
 int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, float* topv, int32_t* topi,
-                               int* nsplit_out, float* guard_out, cudaStream_t st);  // stage1_tc.cu
+                               int* nsplit_out, float* guard_rel_out, cudaStream_t st);  // stage1_tc.cu
 
 int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe, int32_t* d_cells,
                         float* d_scores, cudaStream_t st) {
@@ -252,12 +257,12 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
   int32_t* topi = ix->topr_idx.as<int32_t>();
   int32_t* flags = ix->flags.as<int32_t>();
   int32_t* flagged = flags + nrows;  // [0] = count, [1..] = row ids
-  float guard = 1e-5f;
+  float guard = 1e-5f, guard_rel = 0.f;
 
   bool used_tc = false;
   if (ix->opt_stage1_impl != 1) {
-    int32_t s = cb_stage1_tc_shortlist(ix, dQ, nrows, topv, topi, &nsplit, &guard, st);
-    if (s == CB_OK) used_tc = true;
+    int32_t s = cb_stage1_tc_shortlist(ix, dQ, nrows, topv, topi, &nsplit, &guard_rel, st);
+    if (s == CB_OK) { used_tc = true; ix->st_s1_tc_rows += (double)nrows; }
     else if (s != CB_ERR_UNSUPPORTED || ix->opt_stage1_impl == 2) return s;
   }
   if (!used_tc) {
@@ -266,7 +271,7 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
     CB_LAUNCH_CHECK();
   }
   k_stage1_rescore<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(dQ, nrows, ix->centroids, ix->dim, nsplit, topv,
-                                                               topi, nprobe, guard, d_cells, d_scores, flags);
+                                                               topi, nprobe, guard, guard_rel, d_cells, d_scores, flags);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemsetAsync(flagged, 0, sizeof(int32_t), st));
   k_compact_flags<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(flags, nrows, flagged);

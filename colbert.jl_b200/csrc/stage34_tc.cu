@@ -59,26 +59,10 @@ struct TcParams {
   const uint32_t* bitmap; const int64_t* list_off; int32_t* cursors; uint64_t* pairs;
 };
 
-// Q fp32 [nq][32][128] -> fp16 in the SWIZZLE_128B K-major shared-memory image of one query,
-// K-blocks interleaved per 8-row group: [4 row groups][2 K-blocks][8 rows][128 B], 16-byte chunk c
-// of row t stored at chunk c ^ (t & 7).  With a stride-byte-offset of 2048 in the MMA descriptor a
-// query is ONE contiguous 8 KB block, i.e. one bulk copy.
-__global__ void k_tc_prep_queries(const float* __restrict__ Q, uint8_t* __restrict__ out, int nq) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (q, t, 8 dims)
-  const int64_t total = (int64_t)nq * TC_T * (TC_DIM / 8);
-  if (i >= total) return;
-  const int c16 = (int)(i % (TC_DIM / 8));   // 16-byte chunk along K: 0..15
-  const int t = (int)((i / (TC_DIM / 8)) % TC_T);
-  const int64_t q = i / ((TC_DIM / 8) * TC_T);
-  const float* src = Q + (q * TC_T + t) * TC_DIM + c16 * 8;
-  __align__(16) __half h[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) h[j] = __float2half_rn(src[j]);
-  const int kb = c16 >> 3, chunk = c16 & 7;
-  uint8_t* dst = out + q * TC_Q_BYTES + (t >> 3) * 2048 + kb * 1024 + (t & 7) * 128 + ((chunk ^ (t & 7)) << 4);
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-}
-
+// Query operand: the fp16 "row image" built by cb_tc_prep_rows (stage1_tc.cu).  Inside it a query
+// (32 rows) is ONE contiguous 8 KB block -- [4 row groups][2 K-blocks][8 rows][128 B], 16-byte
+// chunk c of row t stored at chunk c ^ (t & 7) -- i.e. one bulk copy, addressed by the MMA
+// descriptor with a stride-byte-offset of 2048.
 // lane owns dims 4*lane .. 4*lane+3 of a token: its 4*NBITS packed bits ...
 template <int NBITS>
 __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ emb, int lane) {
@@ -461,11 +445,9 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   CB_REQUIRE(smem <= budget, CB_ERR_UNSUPPORTED, "internal: tcgen05 kernel shared memory does not fit");
 
   // per-batch query tiles (fp16, swizzled)
-  CB_TRY(ix->q_prep.ensure((size_t)nq * TC_Q_BYTES));
-  {
-    const int64_t total = (int64_t)nq * TC_T * (TC_DIM / 8);
-    k_tc_prep_queries<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dQ, ix->q_prep.as<uint8_t>(), nq);
-    CB_LAUNCH_CHECK();
+  if (ix->q_prep_src != dQ || ix->q_prep_rows != (int64_t)nq * TC_T) {   // else: stage 1 already built this image
+    CB_TRY(ix->q_prep.ensure((size_t)nq * TC_Q_BYTES));
+    CB_TRY(cb_tc_prep_rows(dQ, (int64_t)nq * TC_T, (int64_t)nq * TC_T, ix->q_prep.as<uint8_t>(), st));
   }
   TcParams P{};
   P.centroids_h = ix->centroids_h; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;

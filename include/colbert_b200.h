@@ -92,7 +92,8 @@ int32_t cb_set_option(cb_index* index, const char* key, int64_t value);
  * ((query, candidate passage) pairs scored), "pair_embeddings" (sum of doclens over pairs),
  * "flagged_rows" (query tokens whose top-nprobe needed the exact full scan),
  * "ms_stage1", "ms_stage2", "ms_stage34", "ms_stage5", "ms_total" (need option "profile"),
- * "tc_pairs" / "generic_pairs" (pairs scored by the tcgen05 / the generic kernel).
+ * "tc_pairs" / "generic_pairs" (pairs scored by the tcgen05 / the generic kernel),
+ * "stage1_tc_rows" (query tokens whose centroid shortlist came from the tcgen05 stage-1 kernel).
  */
 int32_t cb_get_stat(const cb_index* index, const char* key, double* value);
 

@@ -169,6 +169,48 @@ def test_probe_matches_oracle(tiny):
                 assert np.array_equal(scores[q].reshape(-1), fix)   # bit-exact fixed-order fp32
 
 
+@pytest.mark.parametrize("K,nq", [(300, 5), (1000, 9), (4096, 24)])
+def test_probe_tensor_core_equals_exact_fp32(K, nq):
+    """Stage 1 on tcgen05 (fp16 operands) must pick the cells of the exact fp32 `_topk`
+    (src/utils.jl:327-332): K not a multiple of the 128-centroid tile, row counts not a multiple of
+    the 256-row unit, every nprobe; identical to the SIMT fp32 path bit for bit."""
+    ix = S.make_index(50, K, seed=60 + nq, doclen_mean=10, doclen_std=3, doclen_min=1, doclen_max=20)
+    with make_searcher(ix) as s:
+        for nprobe in (1, 2, 4, 12):
+            Qn = S.make_queries(ix["centroids"], nq, seed=70 + nprobe, nprobe=nprobe)
+            Qj = np.transpose(Qn, (2, 1, 0))
+            s.set_option("stage1_impl", 2)
+            cells_tc, scores_tc = s.probe(Qj, nprobe=nprobe)
+            assert s.stat("stage1_tc_rows") == nq * 32, "tcgen05 stage-1 kernel did not run"
+            s.set_option("stage1_impl", 1)
+            cells_fp, scores_fp = s.probe(Qj, nprobe=nprobe)
+            assert s.stat("stage1_tc_rows") == 0
+            assert np.array_equal(cells_tc, cells_fp) and np.array_equal(scores_tc, scores_fp)
+            for q in range(nq):
+                top = O._topk(O.centroid_scores(Qn[q].T, ix["centroids"].T), nprobe, dims=2)
+                assert np.array_equal(cells_tc[q], top)
+
+
+def test_probe_tensor_core_near_ties_fall_back_to_exact_scan():
+    """More near-identical centroids than the shortlist holds, closer together than fp16 rounding
+    can resolve: the guard must flag those rows and the exact scan decides (ties -> lower id, like
+    `partialsortperm`)."""
+    ix = S.make_index(50, 512, seed=81, doclen_mean=10, doclen_std=3, doclen_min=1, doclen_max=20)
+    cen = ix["centroids"]
+    for i in range(24):                      # 24 > CB_TOPR copies of centroid 7, last-bits differences
+        cen[300 + i] = cen[7]
+        cen[300 + i, i % 128] += np.float32(1e-7 * (i % 5))
+    Q = np.stack([np.concatenate([cen[7:8].repeat(16, axis=0), cen[9:10].repeat(16, axis=0)])])
+    with make_searcher(ix) as s:
+        s.set_option("stage1_impl", 2)
+        cells, scores = s.probe(np.transpose(Q, (2, 1, 0)), nprobe=2)
+        assert s.stat("stage1_tc_rows") == 32 and s.stat("flagged_rows") >= 16
+    fix = np.stack([O.fixed_order_dot(np.repeat(Q[0][t:t + 1], 512, axis=0), cen) for t in range(32)])
+    want = np.stack([np.lexsort((np.arange(512), -fix[t]))[:2] + 1 for t in range(32)])
+    assert np.array_equal(cells[0], want)
+    assert np.array_equal(scores[0], np.take_along_axis(fix, want - 1, axis=1))
+
+
 def test_probe_ties_resolve_to_lower_id():
     # duplicated centroids force exact score ties; `partialsortperm` keeps the lower index
     ix = S.make_index(200, 64, dim=32, seed=3, doclen_mean=6, doclen_std=2, doclen_min=1, doclen_max=10)
