@@ -125,6 +125,7 @@ struct cb_index {
   int opt_force_generic = 0;
   int opt_stage1_impl = 0;
   int opt_profile = 0;
+  int opt_tc_astages = 0;   // query-tile stages of the tcgen05 scoring kernel (0 = default)
 
   // stats of the last search
   long long st_launches = 0;

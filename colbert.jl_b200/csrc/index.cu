@@ -364,6 +364,7 @@ extern "C" int32_t cb_set_option(cb_index* ix, const char* key, int64_t value) {
   if (!strcmp(key, "force_generic")) ix->opt_force_generic = (int)value;
   else if (!strcmp(key, "stage1_impl")) ix->opt_stage1_impl = (int)value;
   else if (!strcmp(key, "profile")) ix->opt_profile = (int)value;
+  else if (!strcmp(key, "tc_astages")) ix->opt_tc_astages = (int)value;
   else { cb_set_error("unknown option '%s'", key); return CB_ERR_BAD_ARG; }
   return CB_OK;
 }

@@ -12,18 +12,25 @@
 //     every query of the batch that holds it as a candidate (its 1024-bit bitmap row).  The packed
 //     index therefore streams from HBM once per batch instead of once per (query, passage) pair,
 //     and decompression cost is amortised over ~17-113 queries.
-//   * MMA orientation: A = 4 queries x 32 tokens (M = 128 rows, fp16, pre-swizzled once per batch
-//     and fetched from L2 by 1-D bulk async copies), B = passage tokens (N = doclen padded to 16,
-//     <= 240), K = dim = 128.  The fp32 accumulator D[128 x N] lives in TMEM; each epilogue
-//     thread owns one (query, token) row, so "max over document tokens" is an in-register max over
-//     its TMEM columns and "sum over query tokens" is one warp reduction.  Padded token rows
-//     duplicate the last real token, so no column masking is needed.
-//   * Warp-specialised, mbarrier-pipelined: warp 0 = scheduler + query-tile loader, warp 1 = MMA
-//     issuer (one thread), warps 4-7 = epilogue (one TMEM lane quarter each), warps 8-15 =
-//     decompression.  Three pipelines: passage tiles (2 buffers), query tiles (3-5 stages), TMEM
+//   * MMA orientation: A = 4 queries x 32 tokens (M = 128 rows; the batch's fp16 "row image" is
+//     L2-resident and a query is one contiguous 8 KB block of it, fetched by 1-D bulk async
+//     copies), B = passage tokens (N = doclen padded to 16, <= 240 per chunk), K = dim = 128.
+//     The fp32 accumulator D[128 x N] lives in TMEM; each epilogue thread owns one (query, token)
+//     row, so "max over document tokens" is an in-register max over its TMEM columns and "sum over
+//     query tokens" is one warp reduction.  Padded token rows duplicate the last real token, so
+//     no column masking is needed.  Passages of 241..480 tokens are two chunks (two accumulators,
+//     one running maximum).
+//   * What bounds it: every (query, passage) pair pulls its 8 KB query tile L2 -> SMEM, and the
+//     chip sustains ~40 B/clk/SM of that (tools/bulk_l2_bw.cu), i.e. >= ~820 clocks per 4-query
+//     group; the MMA of a group is 320-544 clocks and the epilogue less, so the kernel is built to
+//     keep that stream saturated: query tiles 3-4 groups ahead, passages up to 4 ahead.
+//   * Warp-specialised, mbarrier-pipelined: warp 0 = scheduler (candidate lists, ring allocation),
+//     warp 1 = MMA issuer (one thread), warps 2-3 = query-tile loaders, warps 4-7 = epilogue (one
+//     TMEM lane quarter each), warps 8-15 = decompression.  Pipelines: passage entries (4 meta
+//     slots + a variable-size shared-memory ring of operand tiles), query tiles (3-4 stages), TMEM
 //     accumulators (2 x 256 columns).
-// Requires dim = 128, T = 32, nbits in {1, 2, 4}; passages longer than the tile (doclen > 240) and
-// every other shape are scored by the generic kernel (stage34_generic.cu).
+// Requires dim = 128, T = 32, nbits in {1, 2, 4}; longer passages and every other shape are scored
+// by the generic kernel (stage34_generic.cu).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -31,70 +38,120 @@ namespace {
 
 constexpr int TC_THREADS = 512;
 constexpr int TC_DIM = 128, TC_T = 32;
-constexpr int TC_MAX_BROWS = 240;      // passage-tile rows (tokens); multiple of 16
+constexpr int TC_MAX_BROWS = 240;      // rows (tokens) per chunk; multiple of 16, <= 256 TMEM columns
 constexpr int TC_MAX_ASTAGES = 6;
+constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots == tile barriers)
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
-constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query (two 4 KB K-blocks)
+constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 constexpr int TC_NDEC_WARPS = 8;
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 256;
 
-struct Meta {            // per passage-slot, written by warp 0
-  int ncand;             // candidate queries of the passage scored by this kernel (0 = skip)
+struct Meta {            // one passage entry, written by the scheduler
+  int ncand;             // candidate queries of the passage (< 0: end of stream)
   int L;                 // doclen
-  int npad;              // L padded to a multiple of 16
+  int nchunk;            // 1 or 2
+  int n0, n1;            // rows of chunk 0 / 1 (padded to 16)
   int pid;               // local 0-based pid
+  uint32_t b_off;        // byte offset of the operand tile(s) in the ring
+  uint32_t pad_;
+  long long e0;          // first embedding of the passage
   uint16_t q[CB_NQ_CHUNK];
 };
 
 struct Barriers {
-  uint64_t b_full[2], b_empty[2], meta_full[2], meta_empty[2];
+  uint64_t b_full[TC_NSLOT], b_empty[TC_NSLOT], meta_full[TC_NSLOT], meta_empty[TC_NSLOT];
   uint64_t a_full[TC_MAX_ASTAGES], a_empty[TC_MAX_ASTAGES];
   uint64_t d_full[2], d_empty[2];
 };
 
 struct TcParams {
   const __half* centroids_h; const float* weights; const int32_t* codes; const uint8_t* residuals;
-  const int64_t* offsets; int64_t Np; int nbits, R, W, brows, nastages;
-  const uint8_t* qprep;           // [nq][8 KB] swizzled fp16 query tiles
+  const int64_t* offsets; int64_t Np; int R, W, nastages, ring_bytes, long_limit;
+  const uint8_t* qprep;           // query row image: [nq][8 KB]
   const uint32_t* bitmap; const int64_t* list_off; int32_t* cursors; uint64_t* pairs;
 };
 
-// Query operand: the fp16 "row image" built by cb_tc_prep_rows (stage1_tc.cu).  Inside it a query
-// (32 rows) is ONE contiguous 8 KB block -- [4 row groups][2 K-blocks][8 rows][128 B], 16-byte
-// chunk c of row t stored at chunk c ^ (t & 7) -- i.e. one bulk copy, addressed by the MMA
-// descriptor with a stride-byte-offset of 2048.
-// lane owns dims 4*lane .. 4*lane+3 of a token: its 4*NBITS packed bits ...
-template <int NBITS>
-__device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ emb, int lane) {
-  if (NBITS == 2) return emb[lane];
-  if (NBITS == 4) return reinterpret_cast<const uint16_t*>(emb)[lane];
-  return (emb[lane >> 1] >> ((lane & 1) * 4)) & 0xfu;
+// max over 32 / 16 TMEM columns held in registers, folded into 4 independent chains
+__device__ __forceinline__ void fold32(const uint32_t (&r)[32], float& m0, float& m1, float& m2, float& m3) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    m0 = fmaxf(m0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+    m1 = fmaxf(m1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+    m2 = fmaxf(m2, fmaxf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
+    m3 = fmaxf(m3, fmaxf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+  }
 }
-// ... and 8 bytes of the fp16 centroid row
-__device__ __forceinline__ uint2 load_centroid4(const __half* __restrict__ centroids_h, int32_t code, int lane) {
-  return *reinterpret_cast<const uint2*>(centroids_h + (int64_t)code * TC_DIM + lane * 4);
+__device__ __forceinline__ void fold16(const uint32_t (&r)[16], float& m0, float& m1, float& m2, float& m3) {
+  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])));
+  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])));
+  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])));
+  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])));
+  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
 }
-// v = centroid + w[bucket]; v /= (|v| + eps); fp16; store row `row` (and copies up to row2) of the tile
+
+// Half a warp (16 lanes) expands one token: lane l16 owns dims 8*l16 .. 8*l16+7 = one 16-byte
+// chunk of the fp16 operand row.  Its 8*NBITS packed bits ...
 template <int NBITS>
-__device__ __forceinline__ void finish_token(const float* s_w, uint32_t bits, uint2 craw, int lane, uint8_t* tile,
-                                             int row, int kb_stride, int row2) {
-  const __half2 c01 = *reinterpret_cast<const __half2*>(&craw.x), c23 = *reinterpret_cast<const __half2*>(&craw.y);
-  float v[4] = {__low2float(c01), __high2float(c01), __low2float(c23), __high2float(c23)};
+__device__ __forceinline__ uint32_t load_bits8(const uint8_t* __restrict__ emb, int l16) {
+  if (NBITS == 1) return emb[l16];
+  if (NBITS == 2) return reinterpret_cast<const uint16_t*>(emb)[l16];
+  return reinterpret_cast<const uint32_t*>(emb)[l16];
+}
+// ... are expanded through a shared-memory table indexed by packed BYTE: entry = the 8/NBITS bucket
+// weights of the dims packed in that byte (`_unpackbits`/`_unbinarize` + `bucket_weights[idx]`,
+// src/indexing/codecs/residual.jl:709-719: dim d's index sits at bit d*NBITS, LSB first).
+template <int NBITS>
+__device__ __forceinline__ void lookup_weights8(const float* __restrict__ lut, uint32_t bits, float (&w)[8]) {
+  if (NBITS == 1) {
+    const float4 a = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 8 + 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else if (NBITS == 2) {
+    const float4 a = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 4);
+    const float4 b = *reinterpret_cast<const float4*>(lut + ((bits >> 8) & 255u) * 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float2 a = *reinterpret_cast<const float2*>(lut + ((bits >> (8 * j)) & 255u) * 2);
+      w[2 * j] = a.x; w[2 * j + 1] = a.y;
+    }
+  }
+}
+
+// v = centroid + w[bucket]; v /= (|v| + eps) (`decompress` + `_normalize_array!`, residual.jl:776-781,
+// utils.jl:320-325); fp16; one 16-byte chunk of operand row `row` (and of the padding rows up to row2)
+template <int NBITS>
+__device__ __forceinline__ void finish_token(const float* __restrict__ lut, uint32_t bits, uint4 craw, int l16, uint8_t* tile,
+                                             int kb_stride, int row, int row2) {
+  float w[8];
+  lookup_weights8<NBITS>(lut, bits, w);
+  const __half2* ch = reinterpret_cast<const __half2*>(&craw);
+  float v[8];
   float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    v[j] += s_w[(bits >> (j * NBITS)) & ((1u << NBITS) - 1u)];
-    ss = fmaf(v[j], v[j], ss);
+    const float2 c = __half22float2(ch[j]);
+    v[2 * j] = c.x + w[2 * j];
+    v[2 * j + 1] = c.y + w[2 * j + 1];
+    ss = fmaf(v[2 * j], v[2 * j], ss);
+    ss = fmaf(v[2 * j + 1], v[2 * j + 1], ss);
   }
-  ss = cb_warp_sum(ss);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);   // stays inside the 16-lane half
   const float inv = 1.0f / (sqrtf(ss) + 1.1920929e-07f);   // X ./ (norm + eps)
-  const __half2 o01 = __floats2half2_rn(v[0] * inv, v[1] * inv), o23 = __floats2half2_rn(v[2] * inv, v[3] * inv);
-  uint2 o;
-  o.x = *reinterpret_cast<const uint32_t*>(&o01);
-  o.y = *reinterpret_cast<const uint32_t*>(&o23);
-  const int kb = lane >> 4, chunk = (lane >> 1) & 7, half8 = (lane & 1) * 8;
-  uint8_t* base = tile + kb * kb_stride + half8;
-  for (int r = row; r < row2; r++) *reinterpret_cast<uint2*>(base + ptx::sw128_offset(r, chunk)) = o;
+  uint4 o;
+  __half2 h;
+  h = __floats2half2_rn(v[0] * inv, v[1] * inv); o.x = *reinterpret_cast<const uint32_t*>(&h);
+  h = __floats2half2_rn(v[2] * inv, v[3] * inv); o.y = *reinterpret_cast<const uint32_t*>(&h);
+  h = __floats2half2_rn(v[4] * inv, v[5] * inv); o.z = *reinterpret_cast<const uint32_t*>(&h);
+  h = __floats2half2_rn(v[6] * inv, v[7] * inv); o.w = *reinterpret_cast<const uint32_t*>(&h);
+  uint8_t* base = tile + (l16 >> 3) * kb_stride;
+  const int chunk = l16 & 7;
+  for (int r = row; r < row2; r++) *reinterpret_cast<uint4*>(base + ptx::sw128_offset(r, chunk)) = o;
 }
 
 template <int NBITS>
@@ -103,84 +160,187 @@ k_maxsim_tc(TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align the dynamic window by hand
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int brows = P.brows, NA = P.nastages;
-  const int kb_stride_b = brows * 128;                // bytes between the two K-blocks of a passage tile
-  const int b_bytes = 2 * kb_stride_b;
-  uint8_t* b_tile[2] = {smem, smem + b_bytes};
-  uint8_t* a_tile0 = smem + 2 * b_bytes;              // NA stages of 32 KB
-  Meta* meta = reinterpret_cast<Meta*>(a_tile0 + (size_t)NA * TC_A_BYTES);   // [2]
-  Barriers* bar = reinterpret_cast<Barriers*>(meta + 2);
+  const int NA = P.nastages;
+  uint8_t* ring = smem;                                   // P.ring_bytes (multiple of 1024)
+  uint8_t* a_tile0 = smem + P.ring_bytes;                 // NA stages of 32 KB
+  Meta* meta = reinterpret_cast<Meta*>(a_tile0 + (size_t)NA * TC_A_BYTES);   // [TC_NSLOT]
+  Barriers* bar = reinterpret_cast<Barriers*>(meta + TC_NSLOT);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
-  float* s_w = reinterpret_cast<float*>(s_tmem + 4);
+  float* s_lut = reinterpret_cast<float*>(s_tmem + 4);    // [256][8 / NBITS] (16-byte aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < TC_NSLOT; i++) {
       ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS); ptx::mbar_init(&bar->b_empty[i], 1);
       ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], 6);
-      ptx::mbar_init(&bar->d_full[i], 1);             ptx::mbar_init(&bar->d_empty[i], 4);
     }
+    for (int i = 0; i < 2; i++) { ptx::mbar_init(&bar->d_full[i], 1); ptx::mbar_init(&bar->d_empty[i], 4); }
     for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], 1); ptx::mbar_init(&bar->a_empty[i], 1); }
     ptx::fence_barrier_init();
   }
-  if (tid < (1 << NBITS)) s_w[tid] = P.weights[tid];
+  {  // byte -> bucket weights table
+    constexpr int DPB = 8 / NBITS;
+    for (int i = tid; i < 256 * DPB; i += TC_THREADS) {
+      const int byte = i / DPB, j = i % DPB;
+      s_lut[i] = P.weights[(byte >> (j * NBITS)) & ((1 << NBITS) - 1)];
+    }
+  }
   if (warp == 1) ptx::tmem_alloc(s_tmem, TC_TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int64_t first = blockIdx.x, stride = gridDim.x;
-
   // Register budget per warpgroup (setmaxnreg sits at the top of each role's branch so ptxas
   // allocates per role): the epilogue keeps two TMEM load batches in flight, the rest need little.
   if (warp < 4) {
-  ptx::reg_dec<72>();
-  if (warp != 1) {
-    // ===== scheduler (warp 0) + query-tile loaders (warps 0, 2, 3: group u belongs to loader u % 3) =====
-    const int li = (warp == 0) ? 0 : warp - 1;   // loader index 0..2
-    uint32_t u = 0;
-    int s = 0;
-    for (int64_t p = first; p < P.Np; p += stride, s++) {
-      const int slot = s & 1;
-      Meta& m = meta[slot];
-      int ncand;
-      if (warp == 0) {
-        {  // pull the packed bytes of a passage a few iterations ahead from HBM into L2
-          const int64_t pf = p + 4 * stride;
-          if (pf < P.Np) {
-            const int64_t f0 = P.offsets[pf], f1 = P.offsets[pf + 1];
-            const char* r0 = reinterpret_cast<const char*>(P.residuals) + f0 * P.R;
-            const char* c0 = reinterpret_cast<const char*>(P.codes) + f0 * 4;
-            const int64_t rbytes = (f1 - f0) * P.R, cbytes = (f1 - f0) * 4;
-            for (int64_t o = (int64_t)lane * 128; o < rbytes; o += 32 * 128) ptx::prefetch_l2(r0 + o);
-            for (int64_t o = (int64_t)lane * 128; o < cbytes; o += 32 * 128) ptx::prefetch_l2(c0 + o);
-          }
-        }
-        ptx::mbar_wait(&bar->meta_empty[slot], ((s >> 1) & 1) ^ 1, 1);
-        const int L = (int)(P.offsets[p + 1] - P.offsets[p]);
-        uint32_t w = (lane < P.W) ? P.bitmap[p * P.W + lane] : 0u;
-        if (L > brows || L == 0) w = 0u;     // long passages go to the generic kernel
-        const int c = __popc(w);
-        int pre = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-        int base = pre - c;
-        while (w) { const int b = __ffs(w) - 1; w &= w - 1; m.q[base++] = (uint16_t)(lane * 32 + b); }
-        ncand = __shfl_sync(0xffffffffu, pre, 31);
-        if (lane == 0) { m.ncand = ncand; m.L = L; m.npad = (L + 15) & ~15; m.pid = (int)p; }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
-      } else {
-        ptx::mbar_wait(&bar->meta_full[slot], (s >> 1) & 1, 10);
-        ncand = m.ncand;
+  ptx::reg_dec<80>();
+  if (warp == 0) {
+    // ===== scheduler: candidate list, ring allocation and meta of every passage with >= 1 candidate =====
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    uint32_t head = 0;             // next free byte of the ring
+    int e = 0;                     // entry counter
+    int tail = 0;                  // entries < tail are known to have released their tile
+    uint32_t off_h[TC_NSLOT] = {0, 0, 0, 0}, end_h[TC_NSLOT] = {0, 0, 0, 0};   // regions of the last entries, by e & 3
+    // software prefetch of the next passage's header and bitmap words
+    int64_t o0 = 0, o1 = 0;
+    uint32_t wn = 0;
+    if (first < P.Np) {
+      o0 = P.offsets[first]; o1 = P.offsets[first + 1];
+      wn = (lane < P.W) ? P.bitmap[first * P.W + lane] : 0u;
+    }
+    for (int64_t p = first; p < P.Np; p += stride) {
+      const int64_t e0 = o0;
+      const int L = (int)(o1 - o0);
+      uint32_t w = wn;
+      const int64_t pn = p + stride;
+      if (pn < P.Np) {
+        o0 = P.offsets[pn]; o1 = P.offsets[pn + 1];
+        wn = (lane < P.W) ? P.bitmap[pn * P.W + lane] : 0u;
       }
+      {  // pull the packed bytes of a passage a few iterations ahead from HBM into L2
+        const int64_t pf = p + 6 * stride;
+        if (pf < P.Np) {
+          const int64_t f0 = P.offsets[pf], f1 = P.offsets[pf + 1];
+          const char* r0 = reinterpret_cast<const char*>(P.residuals) + f0 * P.R;
+          const char* c0 = reinterpret_cast<const char*>(P.codes) + f0 * 4;
+          const int64_t rbytes = (f1 - f0) * P.R, cbytes = (f1 - f0) * 4;
+          for (int64_t o = (int64_t)lane * 128; o < rbytes; o += 32 * 128) ptx::prefetch_l2(r0 + o);
+          for (int64_t o = (int64_t)lane * 128; o < cbytes; o += 32 * 128) ptx::prefetch_l2(c0 + o);
+        }
+      }
+      if (L <= 0 || L > P.long_limit) w = 0u;          // empty, or too long: the generic kernel scores it
+      if (!__any_sync(0xffffffffu, w != 0u)) continue;  // no query of the batch wants this passage
+      // tile geometry
+      int nchunk = 1, n0 = (L + 15) & ~15, n1 = 0;
+      if (L > TC_MAX_BROWS) {
+        nchunk = 2;
+        n0 = (((L + 1) >> 1) + 15) & ~15;
+        n1 = (L - n0 + 15) & ~15;
+      }
+      const uint32_t bytes = (uint32_t)(n0 + n1) * 256u;
+      // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_empty[slot], ((e >> 2) & 1) ^ 1, 1);
+      if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
+      // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps
+      uint32_t off = head;
+      if (off + bytes > (uint32_t)P.ring_bytes) off = 0;
+      int need = tail;             // entries < need must be free
+#pragma unroll
+      for (int j = 1; j < TC_NSLOT; j++) {
+        const int ej = e - j;
+        if (ej >= tail) {
+          const int sj = ej & (TC_NSLOT - 1);
+          if (off < end_h[sj] && off_h[sj] < off + bytes && need < ej + 1) need = ej + 1;
+        }
+      }
+      for (; tail < need; tail++) ptx::mbar_wait(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> 2) & 1, 2);
+      off_h[slot] = off; end_h[slot] = off + bytes;
+      head = off + bytes;
+      // candidate list
+      Meta& m = meta[slot];
+      const int c = __popc(w);
+      int pre = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+      int base = pre - c;
+      while (w) { const int b = __ffs(w) - 1; w &= w - 1; m.q[base++] = (uint16_t)(lane * 32 + b); }
+      const int ncand = __shfl_sync(0xffffffffu, pre, 31);
+      if (lane == 0) {
+        m.ncand = ncand; m.L = L; m.nchunk = nchunk; m.n0 = n0; m.n1 = n1; m.pid = (int)p; m.b_off = off; m.e0 = e0;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
+      e++;
+    }
+    // end of stream
+    const int slot = e & (TC_NSLOT - 1);
+    ptx::mbar_wait(&bar->meta_empty[slot], ((e >> 2) & 1) ^ 1, 3);
+    if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t a_base_addr = ptx::smem_u32(a_tile0), ring_addr = ptx::smem_u32(ring);
+    uint32_t ua = 0, ud = 0;
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      const uint32_t ph = (e >> 2) & 1;
+      ptx::mbar_wait(&bar->meta_full[slot], ph, 4);
+      const int ncand = meta[slot].ncand;
+      if (ncand < 0) break;
+      const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
+      const uint32_t b_addr = ring_addr + meta[slot].b_off;
+      ptx::mbar_wait(&bar->b_full[slot], ph, 5);
+      ptx::tc_fence_after();
       const int ngroups = (ncand + 3) >> 2;
-      for (int g = 0; g < ngroups; g++, u++) {
-        if ((int)(u % 3) != li) continue;
-        const int st = u % NA;
-        ptx::mbar_wait(&bar->a_empty[st], ((u / NA) & 1) ^ 1, 2);
+      const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
+      // descriptors: the 8 K-steps differ only in the start-address field (low word)
+      const uint64_t db0 = ptx::smem_desc_k_sw128(b_addr, 1024);
+      const uint64_t db1 = ptx::smem_desc_k_sw128(b_addr + n0 * 256, 1024);
+      for (int g = 0; g < ngroups; g++, ua++) {
+        const int st = ua % NA;
+        ptx::mbar_wait(&bar->a_full[st], (ua / NA) & 1, 6);
+        const uint64_t da0 = ptx::smem_desc_k_sw128(a_base_addr + st * TC_A_BYTES, 2048);
+        for (int c = 0; c < nchunk; c++, ud++) {
+          const int ds = ud & 1;
+          ptx::mbar_wait(&bar->d_empty[ds], ((ud >> 1) & 1) ^ 1, 7);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
+          const uint64_t dbc = c ? db1 : db0;
+          const int kbs = (c ? n1 : n0) * 128;        // bytes between the two K-blocks of the chunk tile
+          const uint32_t idesc = c ? idesc1 : idesc0;
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const uint64_t da = da0 + (uint64_t)(((k >> 2) * 1024 + (k & 3) * 32) >> 4);
+              const uint64_t db = dbc + (uint64_t)(((k >> 2) * kbs + (k & 3) * 32) >> 4);
+              ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+            }
+            if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st]);
+            ptx::tc_commit(&bar->d_full[ds]);
+          }
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::tc_commit(&bar->b_empty[slot]);   // after the passage's last MMA retires
+      __syncwarp();
+    }
+  } else {
+    // ===== query-tile loaders (warps 2, 3: group u belongs to loader u & 1) =====
+    const int li = warp - 2;
+    uint32_t ua = 0;
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 8);
+      const Meta& m = meta[slot];
+      const int ncand = m.ncand;
+      if (ncand < 0) break;
+      const int ngroups = (ncand + 3) >> 2;
+      for (int g = 0; g < ngroups; g++, ua++) {
+        if ((int)(ua & 1) != li) continue;
+        const int st = ua % NA;
+        ptx::mbar_wait(&bar->a_empty[st], ((ua / NA) & 1) ^ 1, 9);
         const int nqg = min(4, ncand - g * 4);
         uint8_t* dst = a_tile0 + (size_t)st * TC_A_BYTES;
         const int qv = (lane < nqg) ? (int)m.q[g * 4 + lane] : 0;   // lane j holds query j of the group
@@ -190,59 +350,16 @@ k_maxsim_tc(TcParams P) {
           if (ptx::elect_one()) ptx::bulk_g2s(dst + j * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st]);
         }
       }
-      if (warp != 0) {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
-      }
-    }
-  } else {
-    // ===== MMA issuer (warp 1) =====
-    const uint32_t a_base_addr = ptx::smem_u32(a_tile0);
-    uint32_t u = 0;
-    int s = 0;
-    for (int64_t p = first; p < P.Np; p += stride, s++) {
-      const int slot = s & 1;
-      const uint32_t ph = (s >> 1) & 1;
-      ptx::mbar_wait(&bar->meta_full[slot], ph, 3);
-      const int ncand = meta[slot].ncand, npad = meta[slot].npad;
-      ptx::mbar_wait(&bar->b_full[slot], ph, 4);
-      ptx::tc_fence_after();
-      const int ngroups = (ncand + 3) >> 2;
-      const uint32_t idesc = ptx::idesc_f16(128, npad > 0 ? npad : 16, 0);
-      // descriptors: the 8 K-steps differ only in the start-address field (low word)
-      const uint64_t db0 = ptx::smem_desc_k_sw128(ptx::smem_u32(b_tile[slot]), 1024);
-      for (int g = 0; g < ngroups; g++, u++) {
-        const int st = u % NA, ds = u & 1;
-        ptx::mbar_wait(&bar->a_full[st], (u / NA) & 1, 5);
-        ptx::mbar_wait(&bar->d_empty[ds], ((u >> 1) & 1) ^ 1, 6);
-        ptx::tc_fence_after();
-        const uint64_t da0 = ptx::smem_desc_k_sw128(a_base_addr + st * TC_A_BYTES, 2048);
-        const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint64_t da = da0 + (uint64_t)(((k >> 2) * 1024 + (k & 3) * 32) >> 4);
-            const uint64_t db = db0 + (uint64_t)(((k >> 2) * kb_stride_b + (k & 3) * 32) >> 4);
-            ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
-          }
-          ptx::tc_commit(&bar->a_empty[st]);
-          ptx::tc_commit(&bar->d_full[ds]);
-        }
-        __syncwarp();
-      }
-      if (ptx::elect_one()) {
-        if (ngroups > 0) ptx::tc_commit(&bar->b_empty[slot]);   // after the passage's last MMA retires
-        else ptx::mbar_arrive(&bar->b_empty[slot]);
-      }
       __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
     }
   }
   } else if (warp < 8) {
-    ptx::reg_inc<208>();
+    ptx::reg_inc<176>();
     // ===== epilogue: TMEM -> max over tokens -> sum over query tokens -> pair list =====
-    const int e = warp - 4;                 // TMEM lane quarter == query slot inside the group
-    uint32_t u = 0;
-    int s = 0;
+    const int q4 = warp - 4;                // TMEM lane quarter == query slot inside the group
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    uint32_t ud = 0;
     // Output batching: the (query, key) record of the r-th scored pair of this warp is parked in
     // lane r % 32; every 32 records the whole warp appends them to the per-query lists with 32
     // atomics in flight at once, and the stores that depend on the atomics' results are deferred
@@ -263,68 +380,52 @@ k_maxsim_tc(TcParams P) {
       }
       cnt = 0;
     };
-    for (int64_t p = first; p < P.Np; p += stride, s++) {
-      const int slot = s & 1;
-      ptx::mbar_wait(&bar->meta_full[slot], (s >> 1) & 1, 7);
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 10);
       const Meta& m = meta[slot];
-      const int ncand = m.ncand, npad = m.npad;
+      const int ncand = m.ncand;
+      if (ncand < 0) break;
+      const int nchunk = m.nchunk, n0 = m.n0, n1 = m.n1;
       const uint32_t pid_inv = 0xffffffffu - (uint32_t)m.pid;
       const int ngroups = (ncand + 3) >> 2;
-      for (int g = 0; g < ngroups; g++, u++) {
-        const int ds = u & 1;
-        ptx::mbar_wait(&bar->d_full[ds], (u >> 1) & 1, 8);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ds * TC_D_COLS + ((uint32_t)(e * 32) << 16);
-        // max over the passage's tokens == max over this thread's npad TMEM columns.  TMEM -> RF
-        // bandwidth is the floor of this role, so the loads are software-pipelined: while two
-        // 32-column chunks are being reduced the next two are already in flight.
+      for (int g = 0; g < ngroups; g++) {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 chains: ILP for the ALU pipe
-        const int nch = npad >> 5;               // full 32-column chunks (<= 7)
-        uint32_t ra[32], rb[32], rc[32], rd[32];
-        auto red32 = [&](const uint32_t (&r)[32]) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
-            m2 = fmaxf(m2, fmaxf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
-            m3 = fmaxf(m3, fmaxf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+        for (int c = 0; c < nchunk; c++, ud++) {
+          const int ds = ud & 1;
+          const int ncol = c ? n1 : n0;
+          const int nfull = ncol >> 5;           // full 32-column chunks (<= 7)
+          ptx::mbar_wait(&bar->d_full[ds], (ud >> 1) & 1, 11);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ds * TC_D_COLS + lane_off;
+          // max over the chunk's tokens == max over this thread's ncol TMEM columns; the load of
+          // the next 32 columns is in flight while the current 32 are folded
+          uint32_t ra[32], rb[32], rt[16];
+          if (nfull > 0) ptx::tmem_ld_32x32b_x32(taddr, ra);
+          else ptx::tmem_ld_32x32b_x16(taddr, rt);
+          ptx::tmem_ld_wait();
+          for (int i = 0; i < nfull; i += 2) {
+            if (i + 1 < nfull) ptx::tmem_ld_32x32b_x32(taddr + (i + 1) * 32, rb);
+            else if (ncol & 16) ptx::tmem_ld_32x32b_x16(taddr + nfull * 32, rt);
+            fold32(ra, m0, m1, m2, m3);
+            ptx::tmem_ld_wait();
+            if (i + 1 >= nfull) break;
+            if (i + 2 < nfull) ptx::tmem_ld_32x32b_x32(taddr + (i + 2) * 32, ra);
+            else if (ncol & 16) ptx::tmem_ld_32x32b_x16(taddr + nfull * 32, rt);
+            fold32(rb, m0, m1, m2, m3);
+            ptx::tmem_ld_wait();
           }
-        };
-        if (nch > 0) ptx::tmem_ld_32x32b_x32(taddr, ra);
-        if (nch > 1) ptx::tmem_ld_32x32b_x32(taddr + 32, rb);
-        ptx::tmem_ld_wait();
-        for (int c = 0; c < nch; c += 4) {
-          if (c + 2 < nch) ptx::tmem_ld_32x32b_x32(taddr + (c + 2) * 32, rc);
-          if (c + 3 < nch) ptx::tmem_ld_32x32b_x32(taddr + (c + 3) * 32, rd);
-          red32(ra);
-          if (c + 1 < nch) red32(rb);
-          ptx::tmem_ld_wait();
-          if (c + 4 < nch) ptx::tmem_ld_32x32b_x32(taddr + (c + 4) * 32, ra);
-          if (c + 5 < nch) ptx::tmem_ld_32x32b_x32(taddr + (c + 5) * 32, rb);
-          if (c + 2 < nch) red32(rc);
-          if (c + 3 < nch) red32(rd);
-          ptx::tmem_ld_wait();
-        }
-        if (npad & 16) {
-          uint32_t r2[16];
-          ptx::tmem_ld_32x32b_x16(taddr + nch * 32, r2);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 8) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(r2[i + 2]), __uint_as_float(r2[i + 3])));
-            m2 = fmaxf(m2, fmaxf(__uint_as_float(r2[i + 4]), __uint_as_float(r2[i + 5])));
-            m3 = fmaxf(m3, fmaxf(__uint_as_float(r2[i + 6]), __uint_as_float(r2[i + 7])));
-          }
+          // every column of this accumulator is in registers: hand it back to the MMA issuer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar->d_empty[ds]);
+          if (ncol & 16) fold16(rt, m0, m1, m2, m3);
         }
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->d_empty[ds]);
         // sum over the 32 query tokens: exact integer warp reduction of 2^-23 fixed point
         // (|mx| <= ~1, 32 terms: no overflow; resolution 1.2e-7, far inside the 1e-3 tolerance)
         const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 8388608.0f));
-        const int qi = g * 4 + e;
+        const int qi = g * 4 + q4;
         if (qi < ncand) {
           const float score = (float)isum * (1.0f / 8388608.0f);
           if (lane == (cnt & 31)) {
@@ -340,69 +441,67 @@ k_maxsim_tc(TcParams P) {
     flush();
     flush();
   } else {
-    ptx::reg_dec<88>();
-    // ===== decompression: packed codes/residuals -> normalised fp16 passage tile =====
-    // Memory-level parallelism is what matters here (two dependent global loads per token): the
-    // header, bitmap row and codes of the NEXT passage are fetched while the current one is being
-    // expanded, and tokens are expanded TC_DBATCH at a time with all their loads issued first.
+    ptx::reg_dec<96>();
+    // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
+    // Half a warp per token; memory-level parallelism is what matters (code -> centroid row is a
+    // dependent pair of loads), so tokens are expanded TC_DBATCH pairs at a time with all loads
+    // of a batch issued before any of it is consumed and the codes of the next batch already
+    // requested.
     constexpr int TC_DBATCH = 4;
-    const int dw = warp - 8;
-    int s = 0;
-    int64_t e0 = 0;
-    int L = 0;
-    uint32_t wv = 0;
-    int32_t mycode = 0;      // code of this warp's lane-th token (token index dw + 8 * lane)
-    if (first < P.Np) {
-      e0 = P.offsets[first];
-      L = (int)(P.offsets[first + 1] - e0);
-      wv = (lane < P.W) ? P.bitmap[first * P.W + lane] : 0u;
-      mycode = (dw + TC_NDEC_WARPS * lane < L && L <= brows) ? P.codes[e0 + dw + TC_NDEC_WARPS * lane] : 0;
-    }
-    for (int64_t p = first; p < P.Np; p += stride, s++) {
-      const int slot = s & 1;
-      const int64_t pn = p + stride;
-      int64_t e0n = 0;
-      int Ln = 0;
-      uint32_t wvn = 0;
-      int32_t coden = 0;
-      if (pn < P.Np) {
-        e0n = P.offsets[pn];
-        Ln = (int)(P.offsets[pn + 1] - e0n);
-        wvn = (lane < P.W) ? P.bitmap[pn * P.W + lane] : 0u;
-        coden = (dw + TC_NDEC_WARPS * lane < Ln && Ln <= brows) ? P.codes[e0n + dw + TC_NDEC_WARPS * lane] : 0;
+    const int dw = warp - 8, half = lane >> 4, l16 = lane & 15;
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 12, 20);
+      const Meta& m = meta[slot];
+      if (m.ncand < 0) break;
+      const int L = m.L, n0 = m.n0, n1 = m.n1, nchunk = m.nchunk;
+      const int64_t e0 = m.e0;
+      uint8_t* tile0 = ring + m.b_off;
+      uint8_t* tile1 = tile0 + n0 * 256;
+      const int rows_end = (nchunk == 2) ? n1 : n0;        // padded rows of the LAST chunk
+      // token of this half-warp in round j: t = 2 * (dw + 8 * j) + half
+      const int npairs = (L + 1) >> 1;
+      const int nround = (npairs - dw + TC_NDEC_WARPS - 1) / TC_NDEC_WARPS;   // rounds of this warp (may be <= 0)
+      int32_t code_next[TC_DBATCH];
+#pragma unroll
+      for (int i = 0; i < TC_DBATCH; i++) {
+        const int t = 2 * (dw + TC_NDEC_WARPS * i) + half;
+        code_next[i] = (i < nround && t < L) ? P.codes[e0 + t] : 0;
       }
-      ptx::mbar_wait(&bar->b_empty[slot], ((s >> 1) & 1) ^ 1, 9, 100);
-      // skip passages no query of the batch wants, empty ones and ones too long for the tile
-      if (L > 0 && L <= brows && __any_sync(0xffffffffu, wv != 0u)) {
-        const int npad = (L + 15) & ~15;
-        const int ntok = (L - dw + TC_NDEC_WARPS - 1) / TC_NDEC_WARPS;
-        uint8_t* tile = b_tile[slot];
-        for (int j0 = 0; j0 < ntok; j0 += TC_DBATCH) {
-          uint32_t bits[TC_DBATCH];
-          uint2 cr[TC_DBATCH];
+      for (int j0 = 0; j0 < nround; j0 += TC_DBATCH) {
+        uint32_t bits[TC_DBATCH];
+        uint4 cr[TC_DBATCH];
 #pragma unroll
-          for (int i = 0; i < TC_DBATCH; i++) {
-            const int j = j0 + i;
-            if (j < ntok) {
-              const int32_t code = __shfl_sync(0xffffffffu, mycode, j);
-              bits[i] = load_bits<NBITS>(P.residuals + (e0 + dw + TC_NDEC_WARPS * j) * P.R, lane);
-              cr[i] = load_centroid4(P.centroids_h, code, lane);
-            }
+        for (int i = 0; i < TC_DBATCH; i++) {
+          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + i)) + half;
+          bits[i] = 0u;
+          cr[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (j0 + i < nround && t < L) {
+            bits[i] = load_bits8<NBITS>(P.residuals + (e0 + t) * P.R, l16);
+            cr[i] = *reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM + l16 * 8);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < TC_DBATCH; i++) {
-            const int j = j0 + i;
-            if (j < ntok) {
-              const int row = dw + TC_NDEC_WARPS * j;
-              finish_token<NBITS>(s_w, bits[i], cr[i], lane, tile, row, kb_stride_b, row == L - 1 ? npad : row + 1);
-            }
+        for (int i = 0; i < TC_DBATCH; i++) {
+          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + TC_DBATCH + i)) + half;
+          code_next[i] = (j0 + TC_DBATCH + i < nround && t < L) ? P.codes[e0 + t] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < TC_DBATCH; i++) {
+          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + i)) + half;
+          if (j0 + i < nround) {            // warp-uniform; a half whose token is past the end only joins the shuffles
+            const bool live = t < L;
+            const int c = (live && t >= n0) ? 1 : 0;
+            const int row = t - c * n0;
+            // the last real token also fills the padding rows of its chunk
+            const int row2 = !live ? row : (t == L - 1) ? rows_end : row + 1;
+            finish_token<NBITS>(s_lut, bits[i], cr[i], l16, c ? tile1 : tile0, (c ? n1 : n0) * 128, row, row2);
           }
         }
       }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->b_full[slot]);
-      e0 = e0n; L = Ln; wv = wvn; mycode = coden;
     }
   }
 
@@ -414,8 +513,8 @@ k_maxsim_tc(TcParams P) {
   }
 }
 
-size_t tc_smem_bytes(int brows, int nastages) {
-  return 1024 + (size_t)2 * 2 * brows * 128 + (size_t)nastages * TC_A_BYTES + 2 * sizeof(Meta) + sizeof(Barriers) + 16 + 64;
+size_t tc_fixed_smem_bytes(int nbits) {
+  return 1024 + (size_t)TC_NSLOT * sizeof(Meta) + sizeof(Barriers) + 16 + (size_t)256 * (8 / nbits) * 4 + 64;
 }
 
 }  // namespace
@@ -434,24 +533,33 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
                       const int64_t* d_list_off, int32_t* d_cursors, uint64_t* d_pairs, cudaStream_t st) {
   CB_REQUIRE(cb_stage34_tc_supported(ix, T), CB_ERR_UNSUPPORTED, "shape not supported by the tcgen05 scoring kernel");
   if (nq == 0 || ix->Np == 0) return CB_OK;
-  // tile geometry: as many query-tile stages as fit beside two passage tiles
-  int brows = (int)((ix->max_doclen + 15) & ~(int64_t)15);
-  if (brows > TC_MAX_BROWS) brows = TC_MAX_BROWS;
-  if (brows < 16) brows = 16;
+  // shared-memory split: query-tile stages vs. the operand-tile ring
   const size_t budget = 232448;  // 227 KB opt-in shared memory per CTA on sm_100
-  int nast = TC_MAX_ASTAGES;
-  while (nast > 2 && tc_smem_bytes(brows, nast) > budget) nast--;
-  const size_t smem = tc_smem_bytes(brows, nast);
-  CB_REQUIRE(smem <= budget, CB_ERR_UNSUPPORTED, "internal: tcgen05 kernel shared memory does not fit");
+  int nast = ix->opt_tc_astages > 0 ? ix->opt_tc_astages : 3;
+  if (nast < 2) nast = 2;
+  if (nast > TC_MAX_ASTAGES) nast = TC_MAX_ASTAGES;
+  const size_t fixed = tc_fixed_smem_bytes(ix->nbits);
+  CB_REQUIRE(fixed + (size_t)nast * TC_A_BYTES + 16 * 256 <= budget, CB_ERR_UNSUPPORTED,
+             "internal: tcgen05 kernel shared memory does not fit");
+  const size_t ring = (budget - fixed - (size_t)nast * TC_A_BYTES) & ~(size_t)1023;
+  // the ring must hold the largest passage the kernel takes; longer ones go to the generic kernel
+  int64_t long_limit = 2 * TC_MAX_BROWS;
+  {
+    const int64_t ring_rows = (int64_t)(ring / 256) - 32;    // chunk padding: up to 2 x 15 extra rows
+    if (long_limit > ring_rows) long_limit = ring_rows;
+    if (long_limit < 1) long_limit = 1;
+  }
+  const size_t smem = fixed + (size_t)nast * TC_A_BYTES + ring;
 
-  // per-batch query tiles (fp16, swizzled)
-  if (ix->q_prep_src != dQ || ix->q_prep_rows != (int64_t)nq * TC_T) {   // else: stage 1 already built this image
+  // per-batch query row image (fp16, swizzled): stage 1 has usually built it already
+  if (ix->q_prep_src != dQ || ix->q_prep_rows != (int64_t)nq * TC_T) {
     CB_TRY(ix->q_prep.ensure((size_t)nq * TC_Q_BYTES));
     CB_TRY(cb_tc_prep_rows(dQ, (int64_t)nq * TC_T, (int64_t)nq * TC_T, ix->q_prep.as<uint8_t>(), st));
   }
   TcParams P{};
   P.centroids_h = ix->centroids_h; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;
-  P.offsets = ix->offsets; P.Np = ix->Np; P.nbits = ix->nbits; P.R = ix->R; P.W = W; P.brows = brows; P.nastages = nast;
+  P.offsets = ix->offsets; P.Np = ix->Np; P.R = ix->R; P.W = W; P.nastages = nast;
+  P.ring_bytes = (int)ring; P.long_limit = (int)long_limit;
   P.qprep = ix->q_prep.as<uint8_t>(); P.bitmap = d_bitmap; P.list_off = d_list_off; P.cursors = d_cursors; P.pairs = d_pairs;
   int64_t grid = ix->sm_count;
   if (grid > ix->Np) grid = ix->Np;
@@ -467,19 +575,19 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   CB_LAUNCH_CHECK();
   ix->st_tc_pairs = ix->st_pairs;
 
-  // passages longer than the tile: generic kernel on just those
-  if (ix->max_doclen > brows) {
-    if (ix->n_long < 0 || ix->long_limit != brows) {   // the list is a property of the index: build once
+  // passages longer than the kernel takes: generic kernel on just those
+  if (ix->max_doclen > long_limit) {
+    if (ix->n_long < 0 || ix->long_limit != (int32_t)long_limit) {   // the list is a property of the index: build once
       CB_TRY(ix->long_list.ensure(sizeof(int32_t) * (size_t)(ix->Np + 1)));
       int32_t* d_long = ix->long_list.as<int32_t>();
       CB_CUDA(cudaMemsetAsync(d_long, 0, sizeof(int32_t), st));
-      k_collect_long_tc<<<(unsigned)((ix->Np + 255) / 256), 256, 0, st>>>(ix->offsets, ix->Np, brows, d_long);
+      k_collect_long_tc<<<(unsigned)((ix->Np + 255) / 256), 256, 0, st>>>(ix->offsets, ix->Np, long_limit, d_long);
       CB_LAUNCH_CHECK();
       int32_t* h = reinterpret_cast<int32_t*>(ix->pinned_total + 5);
       CB_CUDA(cudaMemcpyAsync(h, d_long, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       CB_CUDA(cudaStreamSynchronize(st));
       ix->n_long = *h;
-      ix->long_limit = brows;
+      ix->long_limit = (int32_t)long_limit;
     }
     if (ix->n_long > 0)
       CB_TRY(cb_stage34_generic(ix, dQ, nq, T, W, d_bitmap, ix->long_list.as<int32_t>() + 1, ix->n_long, d_list_off,

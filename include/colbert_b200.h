@@ -83,7 +83,8 @@ int32_t cb_index_info(const cb_index* index, int64_t info[8]);
 /*
  * Tuning / test knobs.  Keys: "force_generic" (1 = use only the generic SIMT scoring kernel),
  * "stage1_impl" (0 = auto, 1 = SIMT fp32, 2 = tcgen05), "profile" (1 = record per-stage CUDA
- * event timings, readable through cb_get_stat).  Unknown key -> CB_ERR_BAD_ARG.
+ * event timings, readable through cb_get_stat), "tc_astages" (query-tile pipeline stages of the
+ * tcgen05 scoring kernel, 2..6; 0 = default).  Unknown key -> CB_ERR_BAD_ARG.
  */
 int32_t cb_set_option(cb_index* index, const char* key, int64_t value);
 
