@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=3, help="queries timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true", help="score with the generic SIMT kernel only")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (cb_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -72,10 +73,9 @@ def gen_global(torch, wl, dev):
 
 
 def shard_bounds(torch, csum, n):
-    total = int(csum[-1])
-    targets = torch.tensor([total * r // n for r in range(1, n)], dtype=torch.int64, device=csum.device)
-    cuts = torch.searchsorted(csum, targets).tolist() if n > 1 else []
-    return [0] + [int(c) for c in cuts] + [csum.numel() - 1]
+    """Contiguous passage ranges balanced by embedding count (colbert.jl_b200/sharding.py)."""
+    from colbert_jl_b200 import sharding as SH
+    return SH.shard_bounds(csum.cpu().numpy(), n)
 
 
 def gen_shard(torch, wl, dev, csum, lo, hi, nbits):
@@ -255,6 +255,9 @@ def main():
     t_build = time.perf_counter() - t_build
     if args.force_generic:
         s.set_option("force_generic", 1)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        s.set_option(key, int(val))
     keep_for_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
     if not keep_for_cpu:
         del codes, res
@@ -263,20 +266,14 @@ def main():
     out_p = torch.zeros((nq, k), dtype=torch.int64, device=dev)
     out_s = torch.zeros((nq, k), dtype=torch.float32, device=dev)
     out_c = torch.zeros((nq,), dtype=torch.int32, device=dev)
-    if world > 1:
-        all_p = torch.zeros((world, nq, k), dtype=torch.int64, device=dev)
-        all_s = torch.zeros((world, nq, k), dtype=torch.float32, device=dev)
-        mrg_p, mrg_s = torch.zeros_like(out_p), torch.zeros_like(out_s)
+    from colbert_jl_b200 import sharding as SH
+    sharded = SH.ShardedSearcher(s)
+    loc_p, loc_s = torch.zeros_like(out_p), torch.zeros_like(out_s)   # per-shard lists (world > 1)
     lib = cb.load()
     stream = torch.cuda.current_stream().cuda_stream
 
-    def step():
-        s.search_batch_device(Qd.data_ptr(), nq, T, k, out_p.data_ptr(), out_s.data_ptr(), out_c.data_ptr(), stream=stream)
-        if world > 1:   # only the per-shard top-k lists cross NVLink
-            dist.all_gather_into_tensor(all_p, out_p)
-            dist.all_gather_into_tensor(all_s, out_s)
-            cb._lib.check(lib.cb_merge_topk_device(local, world, nq, k, all_p.data_ptr(), all_s.data_ptr(),
-                                                   mrg_p.data_ptr(), mrg_s.data_ptr(), stream))
+    def step():   # world > 1: local search, all-gather of the per-shard top-k lists (NCCL), merge kernel
+        sharded.search_batch_device(Qd, k, out_p, out_s, out_c, stream=stream, local_p=loc_p, local_s=loc_s)
 
     def barrier():
         torch.cuda.synchronize()
@@ -317,13 +314,9 @@ def main():
             cb._lib.check(lib.cb_search_batch(s._h, Qh.data_ptr(), nq, T, args.nprobe, k, hp.data_ptr(), hs.data_ptr(), hc.data_ptr()))
         else:
             Qd2.copy_(Qh, non_blocking=True)
-            s.search_batch_device(Qd2.data_ptr(), nq, T, k, out_p.data_ptr(), out_s.data_ptr(), out_c.data_ptr(), stream=stream)
-            dist.all_gather_into_tensor(all_p, out_p)
-            dist.all_gather_into_tensor(all_s, out_s)
-            cb._lib.check(lib.cb_merge_topk_device(local, world, nq, k, all_p.data_ptr(), all_s.data_ptr(),
-                                                   mrg_p.data_ptr(), mrg_s.data_ptr(), stream))
-            hp.copy_(mrg_p, non_blocking=True)
-            hs.copy_(mrg_s, non_blocking=True)
+            sharded.search_batch_device(Qd2, k, out_p, out_s, out_c, stream=stream, local_p=loc_p, local_s=loc_s)
+            hp.copy_(out_p, non_blocking=True)
+            hs.copy_(out_s, non_blocking=True)
             hc.copy_(out_c, non_blocking=True)
             torch.cuda.synchronize()
 

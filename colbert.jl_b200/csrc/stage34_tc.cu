@@ -44,6 +44,7 @@ constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots 
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
 constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 constexpr int TC_NDEC_WARPS = 8;
+constexpr int TC_NTEAMS = 2;            // decompression teams (alternate passages)
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 256;
 
 struct Meta {            // one passage entry, written by the scheduler
@@ -92,66 +93,88 @@ __device__ __forceinline__ void fold16(const uint32_t (&r)[16], float& m0, float
   m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
 }
 
-// Half a warp (16 lanes) expands one token: lane l16 owns dims 8*l16 .. 8*l16+7 = one 16-byte
-// chunk of the fp16 operand row.  Its 8*NBITS packed bits ...
+// Decompression helpers.  EIGHT lanes expand one token (a warp expands 4 tokens at a time): lane l8
+// owns dims 16*l8 .. 16*l8+15 = two adjacent 16-byte chunks of the fp16 operand row.  Its 16*NBITS
+// packed bits ...
+template <int NBITS> struct Bits16;
+template <> struct Bits16<1> { uint32_t v; };        // 2 bytes
+template <> struct Bits16<2> { uint32_t v; };        // 4 bytes
+template <> struct Bits16<4> { uint2 v; };           // 8 bytes
 template <int NBITS>
-__device__ __forceinline__ uint32_t load_bits8(const uint8_t* __restrict__ emb, int l16) {
-  if (NBITS == 1) return emb[l16];
-  if (NBITS == 2) return reinterpret_cast<const uint16_t*>(emb)[l16];
-  return reinterpret_cast<const uint32_t*>(emb)[l16];
+__device__ __forceinline__ Bits16<NBITS> load_bits16(const uint8_t* __restrict__ emb, int l8) {
+  Bits16<NBITS> b;
+  if constexpr (NBITS == 1) b.v = reinterpret_cast<const uint16_t*>(emb)[l8];
+  else if constexpr (NBITS == 2) b.v = reinterpret_cast<const uint32_t*>(emb)[l8];
+  else b.v = reinterpret_cast<const uint2*>(emb)[l8];
+  return b;
 }
 // ... are expanded through a shared-memory table indexed by packed BYTE: entry = the 8/NBITS bucket
 // weights of the dims packed in that byte (`_unpackbits`/`_unbinarize` + `bucket_weights[idx]`,
 // src/indexing/codecs/residual.jl:709-719: dim d's index sits at bit d*NBITS, LSB first).
 template <int NBITS>
-__device__ __forceinline__ void lookup_weights8(const float* __restrict__ lut, uint32_t bits, float (&w)[8]) {
-  if (NBITS == 1) {
-    const float4 a = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 8);
-    const float4 b = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 8 + 4);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-  } else if (NBITS == 2) {
-    const float4 a = *reinterpret_cast<const float4*>(lut + (bits & 255u) * 4);
-    const float4 b = *reinterpret_cast<const float4*>(lut + ((bits >> 8) & 255u) * 4);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-  } else {
+__device__ __forceinline__ void lookup_weights16(const float* __restrict__ lut, const Bits16<NBITS>& b, float (&w)[16]) {
+  if constexpr (NBITS == 1) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const float* e = lut + ((b.v >> (8 * j)) & 255u) * 8;
+      const float4 x = *reinterpret_cast<const float4*>(e), y = *reinterpret_cast<const float4*>(e + 4);
+      w[8 * j] = x.x; w[8 * j + 1] = x.y; w[8 * j + 2] = x.z; w[8 * j + 3] = x.w;
+      w[8 * j + 4] = y.x; w[8 * j + 5] = y.y; w[8 * j + 6] = y.z; w[8 * j + 7] = y.w;
+    }
+  } else if constexpr (NBITS == 2) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float2 a = *reinterpret_cast<const float2*>(lut + ((bits >> (8 * j)) & 255u) * 2);
-      w[2 * j] = a.x; w[2 * j + 1] = a.y;
+      const float4 x = *reinterpret_cast<const float4*>(lut + ((b.v >> (8 * j)) & 255u) * 4);
+      w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t word = j < 4 ? b.v.x : b.v.y;
+      const float2 x = *reinterpret_cast<const float2*>(lut + ((word >> (8 * (j & 3))) & 255u) * 2);
+      w[2 * j] = x.x; w[2 * j + 1] = x.y;
     }
   }
 }
 
 // v = centroid + w[bucket]; v /= (|v| + eps) (`decompress` + `_normalize_array!`, residual.jl:776-781,
-// utils.jl:320-325); fp16; one 16-byte chunk of operand row `row` (and of the padding rows up to row2)
+// utils.jl:320-325) in fp32, rounded to fp16 once; this lane's two 16-byte chunks of operand row `row`.
 template <int NBITS>
-__device__ __forceinline__ void finish_token(const float* __restrict__ lut, uint32_t bits, uint4 craw, int l16, uint8_t* tile,
-                                             int kb_stride, int row, int row2) {
-  float w[8];
-  lookup_weights8<NBITS>(lut, bits, w);
-  const __half2* ch = reinterpret_cast<const __half2*>(&craw);
-  float v[8];
-  float ss = 0.f;
+__device__ __forceinline__ void finish_token16(const float* __restrict__ lut, const Bits16<NBITS>& bits, const uint4 (&craw)[2],
+                                               int l8, uint8_t* tile, int kb_stride, int row) {
+  float w[16];
+  lookup_weights16<NBITS>(lut, bits, w);
+  float v[16];
+  float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const float2 c = __half22float2(ch[j]);
-    v[2 * j] = c.x + w[2 * j];
-    v[2 * j + 1] = c.y + w[2 * j + 1];
-    ss = fmaf(v[2 * j], v[2 * j], ss);
-    ss = fmaf(v[2 * j + 1], v[2 * j + 1], ss);
+  for (int h = 0; h < 2; h++) {
+    const __half2* ch = reinterpret_cast<const __half2*>(&craw[h]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float2 c = __half22float2(ch[j]);
+      const int d = 8 * h + 2 * j;
+      v[d] = c.x + w[d];
+      v[d + 1] = c.y + w[d + 1];
+      ss0 = fmaf(v[d], v[d], ss0);
+      ss1 = fmaf(v[d + 1], v[d + 1], ss1);
+    }
   }
+  float ss = ss0 + ss1;
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);   // stays inside the 16-lane half
+  for (int o = 4; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);   // stays inside the 8-lane group
   const float inv = 1.0f / (sqrtf(ss) + 1.1920929e-07f);   // X ./ (norm + eps)
-  uint4 o;
-  __half2 h;
-  h = __floats2half2_rn(v[0] * inv, v[1] * inv); o.x = *reinterpret_cast<const uint32_t*>(&h);
-  h = __floats2half2_rn(v[2] * inv, v[3] * inv); o.y = *reinterpret_cast<const uint32_t*>(&h);
-  h = __floats2half2_rn(v[4] * inv, v[5] * inv); o.z = *reinterpret_cast<const uint32_t*>(&h);
-  h = __floats2half2_rn(v[6] * inv, v[7] * inv); o.w = *reinterpret_cast<const uint32_t*>(&h);
-  uint8_t* base = tile + (l16 >> 3) * kb_stride;
-  const int chunk = l16 & 7;
-  for (int r = row; r < row2; r++) *reinterpret_cast<uint4*>(base + ptx::sw128_offset(r, chunk)) = o;
+  uint8_t* base = tile + (l8 >> 2) * kb_stride + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint4 o;
+    __half2 t;
+    t = __floats2half2_rn(v[8 * h + 0] * inv, v[8 * h + 1] * inv); o.x = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2half2_rn(v[8 * h + 2] * inv, v[8 * h + 3] * inv); o.y = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2half2_rn(v[8 * h + 4] * inv, v[8 * h + 5] * inv); o.z = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2half2_rn(v[8 * h + 6] * inv, v[8 * h + 7] * inv); o.w = *reinterpret_cast<const uint32_t*>(&t);
+    const int chunk = ((2 * l8 + h) & 7) ^ (row & 7);      // SWIZZLE_128B: 16-byte chunk c of row r sits at c ^ (r & 7)
+    *reinterpret_cast<uint4*>(base + (chunk << 4)) = o;
+  }
 }
 
 template <int NBITS>
@@ -172,7 +195,7 @@ k_maxsim_tc(TcParams P) {
 
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
-      ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS); ptx::mbar_init(&bar->b_empty[i], 1);
+      ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], 1);
       ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], 6);
     }
     for (int i = 0; i < 2; i++) { ptx::mbar_init(&bar->d_full[i], 1); ptx::mbar_init(&bar->d_empty[i], 4); }
@@ -280,56 +303,59 @@ k_maxsim_tc(TcParams P) {
     ptx::mbar_wait(&bar->meta_empty[slot], ((e >> 2) & 1) ^ 1, 3);
     if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t a_base_addr = ptx::smem_u32(a_tile0), ring_addr = ptx::smem_u32(ring);
-    uint32_t ua = 0, ud = 0;
-    for (int e = 0;; e++) {
-      const int slot = e & (TC_NSLOT - 1);
-      const uint32_t ph = (e >> 2) & 1;
-      ptx::mbar_wait(&bar->meta_full[slot], ph, 4);
-      const int ncand = meta[slot].ncand;
-      if (ncand < 0) break;
-      const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
-      const uint32_t b_addr = ring_addr + meta[slot].b_off;
-      ptx::mbar_wait(&bar->b_full[slot], ph, 5);
-      ptx::tc_fence_after();
-      const int ngroups = (ncand + 3) >> 2;
-      const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
-      // descriptors: the 8 K-steps differ only in the start-address field (low word)
-      const uint64_t db0 = ptx::smem_desc_k_sw128(b_addr, 1024);
-      const uint64_t db1 = ptx::smem_desc_k_sw128(b_addr + n0 * 256, 1024);
-      for (int g = 0; g < ngroups; g++, ua++) {
-        const int st = ua % NA;
-        ptx::mbar_wait(&bar->a_full[st], (ua / NA) & 1, 6);
-        const uint64_t da0 = ptx::smem_desc_k_sw128(a_base_addr + st * TC_A_BYTES, 2048);
-        for (int c = 0; c < nchunk; c++, ud++) {
-          const int ds = ud & 1;
-          ptx::mbar_wait(&bar->d_empty[ds], ((ud >> 1) & 1) ^ 1, 7);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
-          const uint64_t dbc = c ? db1 : db0;
-          const int kbs = (c ? n1 : n0) * 128;        // bytes between the two K-blocks of the chunk tile
-          const uint32_t idesc = c ? idesc1 : idesc0;
-          if (ptx::elect_one()) {
+    // ===== MMA issuer: ONE elected thread runs the whole loop (no per-group elect / reconvergence);
+    // stage and parity counters are carried incrementally and every descriptor is a precomputed low
+    // word plus a constant, so a group costs a few dozen instructions.  The issuer is the serial
+    // resource of the kernel: at N = 80 a group's 8 MMAs are only ~320 tensor clocks. =====
+    if (ptx::elect_one()) {
+      const uint32_t a_lo0 = ((ptx::smem_u32(a_tile0) & 0x3ffffu) >> 4) | (1u << 16);   // descriptor low words: start
+      const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);    // address >> 4, LBO field = 1
+      constexpr uint32_t HI_A = (2048u >> 4) | (1u << 14) | (2u << 29);   // SBO 2048 | version 1 | SWIZZLE_128B
+      constexpr uint32_t HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024
+      uint32_t st = 0, a_par = 0;        // query-tile stage / parity of its next a_full phase
+      uint32_t ds = 0, d_par = 1;        // accumulator / parity of its next d_empty phase
+      for (int e = 0;; e++) {
+        const int slot = e & (TC_NSLOT - 1);
+        const uint32_t ph = (e >> 2) & 1;
+        ptx::mbar_wait(&bar->meta_full[slot], ph, 4);
+        const int ncand = meta[slot].ncand;
+        if (ncand < 0) break;
+        const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
+        const uint32_t b_lo0 = ring_lo + (meta[slot].b_off >> 4);
+        const uint32_t b_lo1 = b_lo0 + (uint32_t)n0 * 16u;                 // chunk 1 starts n0 * 256 bytes in
+        const uint32_t kb0 = (uint32_t)n0 * 8u, kb1 = (uint32_t)n1 * 8u;   // K-block stride (rows * 128 B) >> 4
+        const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
+        const int ngroups = (ncand + 3) >> 2;
+        ptx::mbar_wait(&bar->b_full[slot], ph, 5);
+        for (int g = 0; g < ngroups; g++) {
+          ptx::mbar_wait(&bar->a_full[st], a_par, 6);
+          const uint32_t a_lo = a_lo0 + st * (uint32_t)(TC_A_BYTES >> 4);
+          for (int c = 0; c < nchunk; c++) {
+            ptx::mbar_wait(&bar->d_empty[ds], d_par, 7);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
+            const uint32_t b_lo = c ? b_lo1 : b_lo0, kb = c ? kb1 : kb0, idesc = c ? idesc1 : idesc0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              const uint64_t da = da0 + (uint64_t)(((k >> 2) * 1024 + (k & 3) * 32) >> 4);
-              const uint64_t db = dbc + (uint64_t)(((k >> 2) * kbs + (k & 3) * 32) >> 4);
+              const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
+              const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
               ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
             }
             if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st]);
             ptx::tc_commit(&bar->d_full[ds]);
+            ds ^= 1u;
+            d_par ^= (ds == 0u) ? 1u : 0u;
           }
-          __syncwarp();
+          if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
         }
+        ptx::tc_commit(&bar->b_empty[slot]);   // arrives after the passage's last MMA retires
       }
-      if (ptx::elect_one()) ptx::tc_commit(&bar->b_empty[slot]);   // after the passage's last MMA retires
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ===== query-tile loaders (warps 2, 3: group u belongs to loader u & 1) =====
     const int li = warp - 2;
-    uint32_t ua = 0;
+    uint32_t ua = 0, st = 0, a_par = 1;   // stage of group ua / parity of its next a_empty phase
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
       ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 8);
@@ -338,16 +364,17 @@ k_maxsim_tc(TcParams P) {
       if (ncand < 0) break;
       const int ngroups = (ncand + 3) >> 2;
       for (int g = 0; g < ngroups; g++, ua++) {
+        const uint32_t st_g = st, par_g = a_par;
+        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
         if ((int)(ua & 1) != li) continue;
-        const int st = ua % NA;
-        ptx::mbar_wait(&bar->a_empty[st], ((ua / NA) & 1) ^ 1, 9);
+        ptx::mbar_wait(&bar->a_empty[st_g], par_g, 9);
         const int nqg = min(4, ncand - g * 4);
-        uint8_t* dst = a_tile0 + (size_t)st * TC_A_BYTES;
+        uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
         const int qv = (lane < nqg) ? (int)m.q[g * 4 + lane] : 0;   // lane j holds query j of the group
-        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st], (uint32_t)nqg * TC_Q_BYTES);
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nqg * TC_Q_BYTES);
         for (int j = 0; j < nqg; j++) {
           const int q = __shfl_sync(0xffffffffu, qv, j);
-          if (ptx::elect_one()) ptx::bulk_g2s(dst + j * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st]);
+          if (ptx::elect_one()) ptx::bulk_g2s(dst + j * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
         }
       }
       __syncwarp();
@@ -441,61 +468,70 @@ k_maxsim_tc(TcParams P) {
     flush();
     flush();
   } else {
-    ptx::reg_dec<96>();
+    ptx::reg_dec<112>();
     // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
-    // Half a warp per token; memory-level parallelism is what matters (code -> centroid row is a
-    // dependent pair of loads), so tokens are expanded TC_DBATCH pairs at a time with all loads
-    // of a batch issued before any of it is consumed and the codes of the next batch already
-    // requested.
-    constexpr int TC_DBATCH = 4;
-    const int dw = warp - 8, half = lane >> 4, l16 = lane & 15;
-    for (int e = 0;; e++) {
+    // Eight lanes per token, four tokens per warp-round (fewer, wider instructions per token than a
+    // finer split).  What matters besides instruction count is memory-level parallelism (code ->
+    // centroid row is a dependent pair of loads, ~1-2k clocks under load), so (a) the eight warps
+    // form TC_NTEAMS teams that expand alternate passages concurrently, and (b) a team expands a
+    // passage in balanced batches of up to TC_DBATCH rounds with every load of a batch issued
+    // before any of it is consumed and the codes of the next batch already requested.  Operand
+    // rows past the last token (padding to 16) re-expand the last token: no column masking later.
+    constexpr int TC_DBATCH = 5;
+    constexpr int TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
+    const int team = (warp - 8) / TEAM_WARPS, dw = (warp - 8) % TEAM_WARPS, l8 = lane & 7;
+    for (int e = team;; e += TC_NTEAMS) {
+      // an entry of another team between this team's previous entry and e may end the stream
+      bool stop = false;
+      for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
+        const int sl = ee & (TC_NSLOT - 1);
+        ptx::mbar_wait(&bar->meta_full[sl], (ee >> 2) & 1, 12, 20);
+        if (meta[sl].ncand < 0) { stop = true; break; }
+      }
+      if (stop) break;
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 12, 20);
       const Meta& m = meta[slot];
-      if (m.ncand < 0) break;
-      const int L = m.L, n0 = m.n0, n1 = m.n1, nchunk = m.nchunk;
+      const int L = m.L, n0 = m.n0, n1 = m.n1;
       const int64_t e0 = m.e0;
       uint8_t* tile0 = ring + m.b_off;
       uint8_t* tile1 = tile0 + n0 * 256;
-      const int rows_end = (nchunk == 2) ? n1 : n0;        // padded rows of the LAST chunk
-      // token of this half-warp in round j: t = 2 * (dw + 8 * j) + half
-      const int npairs = (L + 1) >> 1;
-      const int nround = (npairs - dw + TC_NDEC_WARPS - 1) / TC_NDEC_WARPS;   // rounds of this warp (may be <= 0)
+      const int nrows = n0 + n1;                                    // operand rows (multiple of 16)
+      // operand row of this lane in round j: rr = 4 * (dw + TEAM_WARPS * j) + (lane >> 3)
+      const int rr0 = 4 * dw + (lane >> 3);
+      const int nround = (nrows - 4 * dw + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);   // warp-uniform
+      const int nround_max = (nrows + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);
+      const int nbatch = (nround_max + TC_DBATCH - 1) / TC_DBATCH;
+      const int per = (nround_max + nbatch - 1) / nbatch;           // balanced batch length (<= TC_DBATCH)
       int32_t code_next[TC_DBATCH];
 #pragma unroll
       for (int i = 0; i < TC_DBATCH; i++) {
-        const int t = 2 * (dw + TC_NDEC_WARPS * i) + half;
-        code_next[i] = (i < nround && t < L) ? P.codes[e0 + t] : 0;
+        const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
+        code_next[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
       }
-      for (int j0 = 0; j0 < nround; j0 += TC_DBATCH) {
-        uint32_t bits[TC_DBATCH];
-        uint4 cr[TC_DBATCH];
+      for (int j0 = 0; j0 < nround; j0 += per) {
+        Bits16<NBITS> bits[TC_DBATCH];
+        uint4 cr[TC_DBATCH][2];
 #pragma unroll
         for (int i = 0; i < TC_DBATCH; i++) {
-          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + i)) + half;
-          bits[i] = 0u;
-          cr[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (j0 + i < nround && t < L) {
-            bits[i] = load_bits8<NBITS>(P.residuals + (e0 + t) * P.R, l16);
-            cr[i] = *reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM + l16 * 8);
+          if (i < per && j0 + i < nround) {
+            const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + i), L - 1);
+            bits[i] = load_bits16<NBITS>(P.residuals + (e0 + t) * P.R, l8);
+            const uint4* crow = reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM) + 2 * l8;
+            cr[i][0] = crow[0];
+            cr[i][1] = crow[1];
           }
         }
 #pragma unroll
         for (int i = 0; i < TC_DBATCH; i++) {
-          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + TC_DBATCH + i)) + half;
-          code_next[i] = (j0 + TC_DBATCH + i < nround && t < L) ? P.codes[e0 + t] : 0;
+          const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + per + i), L - 1);
+          code_next[i] = (i < per && j0 + per + i < nround) ? P.codes[e0 + t] : 0;
         }
 #pragma unroll
         for (int i = 0; i < TC_DBATCH; i++) {
-          const int t = 2 * (dw + TC_NDEC_WARPS * (j0 + i)) + half;
-          if (j0 + i < nround) {            // warp-uniform; a half whose token is past the end only joins the shuffles
-            const bool live = t < L;
-            const int c = (live && t >= n0) ? 1 : 0;
-            const int row = t - c * n0;
-            // the last real token also fills the padding rows of its chunk
-            const int row2 = !live ? row : (t == L - 1) ? rows_end : row + 1;
-            finish_token<NBITS>(s_lut, bits[i], cr[i], l16, c ? tile1 : tile0, (c ? n1 : n0) * 128, row, row2);
+          if (i < per && j0 + i < nround) {   // warp-uniform
+            const int rr = rr0 + 4 * TEAM_WARPS * (j0 + i);
+            const int c = rr >= n0 ? 1 : 0;
+            finish_token16<NBITS>(s_lut, bits[i], cr[i], l8, c ? tile1 : tile0, (c ? n1 : n0) * 128, rr - c * n0);
           }
         }
       }

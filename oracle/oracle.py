@@ -463,3 +463,26 @@ def search(index: Index, Q, k, fast=True):
     if k > len(pids):
         raise BoundsError(f"attempt to access {len(pids)}-element Vector at index [1:{k}]")
     return pids[indices][:k], scores[indices][:k]
+
+
+def merge_topk(all_pids, all_scores, k):
+    """Checker for the cross-shard merge (no reference counterpart: the reference is single
+    device).  all_pids / all_scores (n_lists, nq, k'), empty slots pid 0 / -inf.  Every passage
+    lives in exactly one shard and shard pid ranges ascend, so the first k of the stable
+    descending sort over the concatenation of ALL candidates (searching.jl:125-127) is the first
+    k of the per-shard first-k lists under (score desc, pid asc)."""
+    all_pids = np.asarray(all_pids, dtype=np.int64)
+    all_scores = np.asarray(all_scores, dtype=F32)
+    n, nq, _ = all_pids.shape
+    out_p = np.zeros((nq, k), dtype=np.int64)
+    out_s = np.full((nq, k), -np.inf, dtype=F32)
+    for q in range(nq):
+        p = all_pids[:, q, :].reshape(-1)
+        s = all_scores[:, q, :].reshape(-1)
+        keep = p > 0
+        p, s = p[keep], s[keep]
+        order = np.lexsort((p, -s.astype(np.float64)))   # score desc, then pid asc
+        m = min(k, len(order))
+        out_p[q, :m] = p[order[:m]]
+        out_s[q, :m] = s[order[:m]]
+    return out_p, out_s
