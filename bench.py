@@ -330,7 +330,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = nq * args.steps / float(t_e2e.item())
-    if world == 1:
+    if world == 1 and not any(kv.startswith("tc_ablate") for kv in args.opt):   # (ablation runs compute garbage on purpose)
         assert torch.equal(hp.to(dev), out_p) and torch.equal(hs.to(dev), out_s), "host and device entry points disagree"
 
     # ---- roofline of the dominant kernel (fused decompress + MaxSim), CUDA events on its stream
@@ -349,8 +349,14 @@ def main():
     alg_bytes = pair_embs * (4 + R) + pairs * 16 + nq * k * 12
     t34 = prof["ms_stage34"] * 1e-3
     tf = flops / t34 / 1e12 if t34 > 0 else 0.0
+    traffic = None    # dram__bytes_read + write of one launch, from the committed ncu --set full capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1 and not args.force_generic:
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(f"{args.workload}:nbits={args.nbits}")
     roofline = {"kernel": "k_maxsim_tc (fused decompress + MaxSim, tcgen05)", "bound": "tensor", "achieved": tf,
-                "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] +
+                "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"], "traffic": traffic,
+                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"] +
                 ", sustained bf16 (kernel runs inside a long step; fp16 and bf16 share the tcgen05 rate)",
                 "hbm_equiv": {"achieved": alg_bytes / t34 / 1e9 if t34 > 0 else 0.0, "peak": pk["hbm"], "unit": "GB/s",
                               "frac": (alg_bytes / t34 / 1e9) / pk["hbm"] if t34 > 0 else 0.0,

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcolbert_b200.so")
+LIB_PATH = os.environ.get("COLBERT_B200_LIB") or os.path.join(_HERE, "lib", "libcolbert_b200.so")   # env override: A/B builds
 
 CB_OK, CB_ERR_BAD_ARG, CB_ERR_DOMAIN, CB_ERR_CUDA, CB_ERR_OOM, CB_ERR_UNSUPPORTED, CB_ERR_BOUNDS = range(7)
 CB_FLAG_DEVICE_POINTERS = 1
