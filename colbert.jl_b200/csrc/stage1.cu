@@ -120,8 +120,8 @@ __device__ __forceinline__ bool s1_better(float sa, int32_t ia, float sb, int32_
 
 __global__ void __launch_bounds__(128)
 k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __restrict__ C, int dim, int nsplit,
-                 const float* __restrict__ topv, const int32_t* __restrict__ topi, int nprobe, float guard,
-                 float guard_rel, int32_t* __restrict__ cells, float* __restrict__ cell_scores, int32_t* __restrict__ flags) {
+                 const float* __restrict__ topv, const int32_t* __restrict__ topi, const float* __restrict__ thr0,
+                 int nprobe, float guard, float guard_rel, int32_t* __restrict__ cells, float* __restrict__ cell_scores, int32_t* __restrict__ flags) {
   int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -145,6 +145,8 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
       if ((ci % CB_TOPR) == CB_TOPR - 1 && cid != 0x7fffffff) excluded = fmaxf(excluded, topv[row * ncand + ci]);
     }
   }
+  // a unit that started from a published threshold dropped everything below it without listing it
+  if (thr0 != nullptr && lane < nsplit) excluded = fmaxf(excluded, thr0[row * nsplit + lane]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) excluded = fmaxf(excluded, __shfl_xor_sync(0xffffffffu, excluded, o));
 
@@ -240,7 +242,7 @@ __global__ void k_compact_flags(const int32_t* __restrict__ flags, int64_t nrows
   }
 }
 
-int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, float* topv, int32_t* topi,
+int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, float* topv, int32_t* topi, float* thr0,
                                int* nsplit_out, float* guard_rel_out, cudaStream_t st);  // stage1_tc.cu
 
 int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe, int32_t* d_cells,
@@ -260,8 +262,10 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
   float guard = 1e-5f, guard_rel = 0.f;
 
   bool used_tc = false;
+  CB_TRY(ix->s1_thr0.ensure(sizeof(float) * nrows * CB_S1_SPLITS));
+  float* thr0 = ix->s1_thr0.as<float>();
   if (ix->opt_stage1_impl != 1) {
-    int32_t s = cb_stage1_tc_shortlist(ix, dQ, nrows, topv, topi, &nsplit, &guard_rel, st);
+    int32_t s = cb_stage1_tc_shortlist(ix, dQ, nrows, topv, topi, thr0, &nsplit, &guard_rel, st);
     if (s == CB_OK) { used_tc = true; ix->st_s1_tc_rows += (double)nrows; }
     else if (s != CB_ERR_UNSUPPORTED || ix->opt_stage1_impl == 2) return s;
   }
@@ -270,8 +274,9 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
     k_stage1_simt<<<grid, 256, 0, st>>>(dQ, nrows, ix->centroids, ix->K, ix->dim, nsplit, topv, topi);
     CB_LAUNCH_CHECK();
   }
-  k_stage1_rescore<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(dQ, nrows, ix->centroids, ix->dim, nsplit, topv,
-                                                               topi, nprobe, guard, guard_rel, d_cells, d_scores, flags);
+  k_stage1_rescore<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(dQ, nrows, ix->centroids, ix->dim, nsplit, topv, topi,
+                                                               used_tc ? thr0 : nullptr, nprobe, guard, guard_rel, d_cells,
+                                                               d_scores, flags);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemsetAsync(flagged, 0, sizeof(int32_t), st));
   k_compact_flags<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(flags, nrows, flagged);

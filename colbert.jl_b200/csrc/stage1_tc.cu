@@ -50,6 +50,8 @@ struct S1Params {
   int64_t nrows, K;
   int n_rowblocks, nsplit, tiles_total, tiles_per_split;
   float* topv; int32_t* topi;   // [nrows][nsplit][CB_TOPR]
+  uint32_t* thr_global;         // [rows_pad] orderable(best known 16th-best approximate score of the row), 0 = none yet
+  float* thr0;                  // [nrows][nsplit] threshold the unit STARTED from (bounds what it dropped unseen)
 };
 
 // fp32 rows -> fp16 row image.  One thread per (row, 16-byte chunk); rows >= nrows are zero.
@@ -190,7 +192,13 @@ k_stage1_tc(S1Params P) {
       const int t0 = split * P.tiles_per_split, t1 = min(P.tiles_total, t0 + P.tiles_per_split);
 #pragma unroll
       for (int j = 0; j < CB_TOPR; j++) { sv[j * S1T_ROWS] = -INFINITY; si[j * S1T_ROWS] = 0x7fffffff; }
-      float thr = -INFINITY;
+      // Start from the best 16th-best score any finished unit of this row has published: a centroid
+      // below it is below >= 16 others, so units of later waves insert almost nothing (without it
+      // every unit re-fills its list from -inf and nearly every 32-column piece takes the slow path).
+      const int64_t grow0 = (int64_t)rb * S1T_ROWS + r;
+      const uint32_t g0 = P.thr_global[grow0];
+      const float thr0 = g0 ? cb_unorderable(g0) : -INFINITY;
+      float thr = thr0;
       for (int t = t0; t < t1; t++, it++) {
         const int ds = it & 1;
         ptx::mbar_wait(&bar->d_full[ds], (it >> 1) & 1, 25);
@@ -212,7 +220,7 @@ k_stage1_tc(S1Params P) {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               const float x = __uint_as_float(v[i]);
-              if (x > thr && (int64_t)(cbase + i) < P.K) thr = s1_insert(sv, si, x, cbase + i);
+              if (x > thr && (int64_t)(cbase + i) < P.K) thr = fmaxf(thr0, s1_insert(sv, si, x, cbase + i));
             }
           }
         }
@@ -221,7 +229,9 @@ k_stage1_tc(S1Params P) {
         if (lane == 0) ptx::mbar_arrive(&bar->d_empty[ds]);
       }
       const int64_t grow = (int64_t)rb * S1T_ROWS + r;
+      if (sv[(CB_TOPR - 1) * S1T_ROWS] > thr0) atomicMax(&P.thr_global[grow], cb_orderable(sv[(CB_TOPR - 1) * S1T_ROWS]));
       if (grow < P.nrows) {
+        P.thr0[grow * P.nsplit + split] = thr0;
         float* ov = P.topv + (grow * P.nsplit + split) * CB_TOPR;
         int32_t* oi = P.topi + (grow * P.nsplit + split) * CB_TOPR;
 #pragma unroll
@@ -251,7 +261,7 @@ int32_t cb_tc_prep_rows(const float* dX, int64_t nrows, int64_t nrows_pad, uint8
   return CB_OK;
 }
 
-int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, float* topv, int32_t* topi,
+int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, float* topv, int32_t* topi, float* thr0,
                                int* nsplit_out, float* guard_rel_out, cudaStream_t st) {
   if (ix->dim != 128 || ix->centroids_img == nullptr) return CB_ERR_UNSUPPORTED;
   static_assert(S1T_SMEM <= 232448, "stage-1 tcgen05 kernel shared memory does not fit");
@@ -277,7 +287,10 @@ int32_t cb_stage1_tc_shortlist(cb_index* ix, const float* dQ, int64_t nrows, flo
   P.tiles_per_split = (P.tiles_total + nsplit - 1) / nsplit;
   nsplit = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;   // drop empty ranges
   P.nsplit = nsplit;
-  P.topv = topv; P.topi = topi;
+  P.topv = topv; P.topi = topi; P.thr0 = thr0;
+  CB_TRY(ix->s1_thr.ensure(sizeof(uint32_t) * (size_t)rows_pad));
+  CB_CUDA(cudaMemsetAsync(ix->s1_thr.p, 0, sizeof(uint32_t) * (size_t)rows_pad, st));
+  P.thr_global = ix->s1_thr.as<uint32_t>();
   const int n_units = P.n_rowblocks * nsplit;
   const int grid = n_units < ix->sm_count ? n_units : ix->sm_count;
   CB_CUDA(cudaFuncSetAttribute(k_stage1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1T_SMEM));
