@@ -247,6 +247,7 @@ def main():
     Qd = gen_queries(torch, cen, nq, T, args.nprobe, dev)
     w = torch.from_numpy(bucket_weights(args.nbits)).to(dev)
     dl = doclens[lo:hi].contiguous()
+    ne_local = codes.numel()
     cfg = cb.ColBERTConfig(dim=dim, nbits=args.nbits, nprobe=args.nprobe, query_maxlen=T)
     torch.cuda.synchronize()
     t_build = time.perf_counter()
@@ -363,6 +364,15 @@ def main():
                               "note": "algorithmic bytes (36 B x pair embeddings + 16 B x pairs) / kernel time; real DRAM "
                                       "traffic is far lower because a passage is decompressed once per batch, not per pair"},
                 "stage_ms": prof, "pairs_per_step": pairs, "pair_embeddings_per_step": pair_embs}
+    # What actually bounds the kernel: every pair pulls its query's 8 KB fp16 tile from L2
+    # into the SM, every indexed embedding its 256 B fp16 centroid row + packed bytes.  Across eight structurally
+    # different builds of the kernel this stream ran at the same ~7.3-8.6 TB/s (ncu l1tex__m_xbar2l1tex_read_bytes
+    # per second), so it is reported next to the HBM / tensor numbers.
+    l2_bytes = pairs * 8192.0 + ne_local * (256.0 + 4 + R)
+    roofline["l2_to_sm"] = {"bytes_per_launch": l2_bytes, "achieved": l2_bytes / t34 / 1e9 if t34 > 0 else 0.0, "unit": "GB/s",
+                            "observed_ceiling": 8600.0,
+                            "note": "8 KB query tile per pair + 292 B per indexed embedding; ceiling = highest "
+                                    "xbar->L1 read rate ncu reported for any build of this kernel (profiles/)"}
 
     # ---- CPU baseline (N = 1, rank 0): the oracle on a bounded sample of the same workload, + parity gate
     cpu = None

@@ -102,7 +102,9 @@ k_stage1_tc(S1Params P) {
   S1Barriers* bar = reinterpret_cast<S1Barriers*>(s_idx + CB_TOPR * S1T_ROWS);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops on the
+  // uniform datapath (no WARPSYNC before the TMEM loads, no divergence checks)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid == 0) {
     ptx::mbar_init(&bar->a_full, 1); ptx::mbar_init(&bar->a_empty, 1);
     for (int i = 0; i < S1T_NB; i++) { ptx::mbar_init(&bar->b_full[i], 1); ptx::mbar_init(&bar->b_empty[i], 1); }

@@ -20,7 +20,12 @@ for i, (ad, src, s, n, r) in enumerate(A):
             m = re.search(r"(IMAD\.MOV\.U32|MOV) R\d+, (RZ, RZ, )?(0x[0-9a-f]+)", A[j][1])
             if m and 0 < int(m.group(3), 16) < 32: tag = int(m.group(3), 16); break
             if "BPT.TRAP" in A[j][1]: break
-        wait = sum(A[j][2] for j in range(i, min(i + 3, len(A))))
+        # the whole wait routine: first try, spin loop (second TRYWAIT, clock reads, compare), up to the trap
+        end = i + 3
+        for j in range(i + 1, min(i + 45, len(A))):
+            if "BPT.TRAP" in A[j][1]: end = j + 1; break
+        if i > 0 and any("TRYWAIT" in A[j][1] for j in range(max(0, i - 12), i)): continue   # the spin-loop TRYWAIT of the previous site
+        wait = sum(A[j][2] for j in range(i, min(end, len(A))))
         sites.append((ad, tag, n, wait))
 agg = collections.OrderedDict()
 for ad, tag, n, w in sites:
