@@ -190,7 +190,23 @@ def time_oracle(oix, Qh, k, n_queries):
     return (time.perf_counter() - t0) / n_queries, results
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there when
+    # NCCL_DEBUG is set): keep the original stdout for the JSON line only and point fd 1 at stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     import torch
     wl = WORKLOADS[args.workload]
@@ -223,7 +239,7 @@ def main():
         sec = float(np.mean(per))
         val = 1.0 / sec
         sample = f"1 query per step ({args.steps} timed) over the full index, numpy/OpenBLAS restatement of ColBERT.jl search"
-        print(json.dumps({"impl": "reference", "metric": "queries/sec", "value": val, "unit": "queries/s", "n_gpus": args.gpus,
+        emit(json.dumps({"impl": "reference", "metric": "queries/sec", "value": val, "unit": "queries/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_out,
                           "cpu_baseline": {"value": val, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
@@ -391,7 +407,7 @@ def main():
         parity = {"queries_checked": nqc, "topk_pids_identical": bool(ok_p), "max_rel_score_err": max_rel, "tolerance": 1e-3}
 
     if rank == 0:
-        print(json.dumps({"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        emit(json.dumps({"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05); f32 exact decisions",
                           "data": "synthetic", "config": cfg_out, "clocks": clocks,
