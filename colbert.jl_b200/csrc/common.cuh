@@ -116,10 +116,14 @@ struct cb_index {
 
   // workspace (grow-only)
   DevBuf q_f32, q_prep, topr_val, topr_idx, cells, cell_scores, flags, bitmap, counts, list_off,
-      cursors, pairs, out_pids, out_scores, out_counts, misc, long_list, hook_a, hook_b, hook_c, s1_thr, s1_thr0;
+      cursors, pairs, out_pids, out_scores, out_counts, misc, long_list, hook_a, hook_b, hook_c, s1_thr, s1_thr0,
+      bitmap2, pl_ents, pl_misc, pl_vec, pl_next, pl_head, pl_top_pids, pl_top_scores, pl_sel, pl_npos;   // PLAID mode (plaid.cu)
   int64_t* pinned_total = nullptr;  // pinned host scalar(s) for the one D2H per batch
   const float* q_prep_src = nullptr; // q_prep currently holds the row image of these query tokens ...
   int64_t q_prep_rows = 0;           // ... (this many rows); reset at the start of every search chunk
+  // what the last cb_stage1_probe left in topr_val / topr_idx / s1_thr0 (read by the PLAID survivor pass)
+  int s1_nsplit = 1, s1_used_tc = 0;
+  float s1_guard = 1e-5f, s1_guard_rel = 0.f;
 
   // options
   int opt_force_generic = 0;
@@ -131,6 +135,7 @@ struct cb_index {
   long long st_launches = 0;
   double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0, st_s1_tc_rows = 0;
   double st_ms[5] = {0, 0, 0, 0, 0};  // stage1, stage2, stage34, stage5, total
+  double st_plaid_survivors = 0, st_plaid_positive = 0, st_plaid_rescored = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -145,6 +150,11 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
 // Stage 2: marks bitmap[pid][W] for every passage in a probed cell; counts[q] = #candidates.
 int32_t cb_stage2_mark(cb_index* ix, const int32_t* d_cells, int nq, int T, int nprobe, int W,
                        uint32_t* d_bitmap, int32_t* d_counts, cudaStream_t st);
+
+// Stages 1+2 for one chunk of <= CB_NQ_CHUNK queries (search.cu): leaves bitmap / counts / list_off / zeroed
+// cursors in the workspace and returns the number of (query, passage) pairs of the chunk.
+int32_t cb_candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int nprobe, int W, cudaStream_t st,
+                            int64_t* total_pairs);
 
 // Exclusive scan of counts -> list offsets (+ total in list_off[nq]).
 int32_t cb_scan_counts(const int32_t* d_counts, int nq, int64_t* d_list_off, cudaStream_t st);

@@ -163,7 +163,8 @@ static void destroy_index(cb_index* ix) {
   DevBuf* bufs[] = {&ix->q_f32, &ix->q_prep, &ix->topr_val, &ix->topr_idx, &ix->cells, &ix->cell_scores,
                     &ix->flags, &ix->bitmap, &ix->counts, &ix->list_off, &ix->cursors, &ix->pairs,
                     &ix->out_pids, &ix->out_scores, &ix->out_counts, &ix->misc, &ix->long_list,
-                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0};
+                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0, &ix->bitmap2, &ix->pl_ents, &ix->pl_misc,
+                    &ix->pl_vec, &ix->pl_next, &ix->pl_head, &ix->pl_top_pids, &ix->pl_top_scores, &ix->pl_sel, &ix->pl_npos};
   for (DevBuf* b : bufs) b->release();
   if (ix->pinned_total) cudaFreeHost(ix->pinned_total);
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
@@ -376,6 +377,9 @@ extern "C" int32_t cb_get_stat(const cb_index* ix, const char* key, double* valu
   else if (!strcmp(key, "pair_embeddings")) *value = ix->st_pair_embs;
   else if (!strcmp(key, "flagged_rows")) *value = ix->st_flagged;
   else if (!strcmp(key, "tc_pairs")) *value = ix->st_tc_pairs;
+  else if (!strcmp(key, "plaid_survivors")) *value = ix->st_plaid_survivors;
+  else if (!strcmp(key, "plaid_candidates")) *value = ix->st_plaid_positive;
+  else if (!strcmp(key, "plaid_rescored")) *value = ix->st_plaid_rescored;
   else if (!strcmp(key, "generic_pairs")) *value = ix->st_generic_pairs;
   else if (!strcmp(key, "stage1_tc_rows")) *value = ix->st_s1_tc_rows;
   else if (!strcmp(key, "ms_stage1")) *value = ix->st_ms[0];

@@ -17,8 +17,8 @@ static int32_t check_query_args(const cb_index* ix, const void* Q, int nq, int T
 
 // stages 1+2 for one chunk of <= CB_NQ_CHUNK queries; leaves bitmap / counts / list_off in the
 // workspace and returns the number of (query, passage) pairs of the chunk.
-static int32_t candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int nprobe, int W, cudaStream_t st,
-                                int64_t* total_pairs) {
+int32_t cb_candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int nprobe, int W, cudaStream_t st,
+                            int64_t* total_pairs) {
   const int64_t nrows = (int64_t)nq * T;
   CB_TRY(ix->cells.ensure(sizeof(int32_t) * nrows * nprobe));
   CB_TRY(ix->cell_scores.ensure(sizeof(float) * nrows * nprobe));
@@ -80,7 +80,7 @@ extern "C" int32_t cb_search_batch_device(cb_index* ix, const float* dQ, int32_t
     const int W = (n + 31) / 32;
     const float* dQc = dQ + (int64_t)q0 * T * ix->dim;
     int64_t total = 0;
-    CB_TRY(candidates_chunk(ix, dQc, n, T, nprobe, W, st, &total));
+    CB_TRY(cb_candidates_chunk(ix, dQc, n, T, nprobe, W, st, &total));
     CB_TRY(ix->pairs.ensure(sizeof(uint64_t) * (size_t)(total > 0 ? total : 1)));
     if (total > 0)
       CB_TRY(cb_stage34_score(ix, dQc, n, T, W, ix->bitmap.as<uint32_t>(), ix->list_off.as<int64_t>(),
@@ -200,7 +200,7 @@ extern "C" int32_t cb_retrieve(cb_index* ix, const float* Q, int32_t T, int32_t 
   CB_TRY(ix->q_f32.ensure(qbytes));
   CB_CUDA(cudaMemcpyAsync(ix->q_f32.p, Q, qbytes, cudaMemcpyHostToDevice, nullptr));
   int64_t total = 0;
-  CB_TRY(candidates_chunk(ix, ix->q_f32.as<float>(), 1, T, nprobe, 1, nullptr, &total));
+  CB_TRY(cb_candidates_chunk(ix, ix->q_f32.as<float>(), 1, T, nprobe, 1, nullptr, &total));
   *out_count = total;
   const int64_t ncopy = total < capacity ? total : capacity;
   if (ncopy > 0) {

@@ -274,6 +274,7 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
     k_stage1_simt<<<grid, 256, 0, st>>>(dQ, nrows, ix->centroids, ix->K, ix->dim, nsplit, topv, topi);
     CB_LAUNCH_CHECK();
   }
+  ix->s1_nsplit = nsplit; ix->s1_used_tc = used_tc ? 1 : 0; ix->s1_guard = guard; ix->s1_guard_rel = guard_rel;
   k_stage1_rescore<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(dQ, nrows, ix->centroids, ix->dim, nsplit, topv, topi,
                                                                used_tc ? thr0 : nullptr, nprobe, guard, guard_rel, d_cells,
                                                                d_scores, flags);

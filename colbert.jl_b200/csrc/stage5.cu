@@ -28,7 +28,7 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, int n_pow2, int t
 }
 
 __global__ void __launch_bounds__(S5_THREADS)
-k_topk_select(const uint64_t* __restrict__ pairs, const int64_t* __restrict__ list_off, int k, int kpow2,
+k_topk_select(const uint64_t* __restrict__ pairs, const int64_t* __restrict__ list_off, const int32_t* __restrict__ lens, int k, int kpow2,
               int64_t pid_base, int64_t* __restrict__ out_pids, float* __restrict__ out_scores) {
   extern __shared__ uint64_t s_sel[];  // kpow2 keys
   __shared__ unsigned int hist[256];
@@ -36,7 +36,7 @@ k_topk_select(const uint64_t* __restrict__ pairs, const int64_t* __restrict__ li
   __shared__ int s_need, s_done, s_cnt;
   const int q = blockIdx.x, tid = threadIdx.x;
   const uint64_t* keys = pairs + list_off[q];
-  const int64_t n = list_off[q + 1] - list_off[q];
+  const int64_t n = lens ? (int64_t)lens[q] : list_off[q + 1] - list_off[q];   // lens: only a prefix of the list is filled
   const int kk = (int)min((int64_t)k, n);
 
   for (int i = tid; i < kpow2; i += S5_THREADS) s_sel[i] = 0ull;
@@ -108,7 +108,19 @@ int32_t cb_stage5_topk(const uint64_t* d_pairs, const int64_t* d_list_off, int n
   CB_REQUIRE(k >= 1 && k <= CB_MAX_K, CB_ERR_UNSUPPORTED, "k must be in 1..%d (got %d)", CB_MAX_K, k);
   if (nq == 0) return CB_OK;
   const int kp = pow2_at_least(k);
-  k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, k, kp, pid_base, d_out_pids,
+  k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, nullptr, k, kp, pid_base, d_out_pids,
+                                                             d_out_scores);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
+}
+
+// Same with explicit per-query list lengths (PLAID mode: only the positive pairs are appended).
+int32_t cb_stage5_topk_lens(const uint64_t* d_pairs, const int64_t* d_list_off, const int32_t* d_lens, int nq, int k,
+                            int64_t pid_base, int64_t* d_out_pids, float* d_out_scores, cudaStream_t st) {
+  CB_REQUIRE(k >= 1 && k <= CB_MAX_K, CB_ERR_UNSUPPORTED, "k must be in 1..%d (got %d)", CB_MAX_K, k);
+  if (nq == 0) return CB_OK;
+  const int kp = pow2_at_least(k);
+  k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, d_lens, k, kp, pid_base, d_out_pids,
                                                              d_out_scores);
   CB_LAUNCH_CHECK();
   return CB_OK;

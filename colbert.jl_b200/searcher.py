@@ -169,6 +169,26 @@ class Searcher:
         L.check(L.load().cb_search_batch_device(self._h, q_ptr, nq, T, nprobe, k, out_pids_ptr, out_scores_ptr,
                                                 out_counts_ptr, stream))
 
+    def search_batch_plaid(self, Q, k: int, ncells: int = 4, centroid_score_threshold: float = 0.4, ndocs: int = 1000):
+        """PLAID-style pruned search (BASELINE config 5; no reference counterpart, semantics in
+        oracle.plaid_search): candidates from `ncells` cells per token, centroid-score threshold
+        pruning, approximate centroid-only scores, the best `ndocs` re-scored exactly, top-k.
+        Q (dim, T, nq) -> (pids (nq, k), scores (nq, k), counts (nq,) = exactly scored passages)."""
+        Qc = self._q_batch(Q)
+        nq, T, _ = Qc.shape
+        pids = np.zeros((nq, k), dtype=np.int64)
+        scores = np.full((nq, k), -np.inf, dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.int32)
+        L.check(L.load().cb_search_batch_plaid(self._h, _ptr(Qc), nq, T, ncells, float(centroid_score_threshold), ndocs, k,
+                                               _ptr(pids), _ptr(scores), _ptr(counts)))
+        return pids, scores, counts
+
+    def search_batch_plaid_device(self, q_ptr, nq, T, k, out_pids_ptr, out_scores_ptr, out_counts_ptr, ncells=4,
+                                  centroid_score_threshold=0.4, ndocs=1000, stream=None):
+        """Device-resident variant of `search_batch_plaid` (raw device pointers, work on `stream`)."""
+        L.check(L.load().cb_search_batch_plaid_device(self._h, q_ptr, nq, T, ncells, float(centroid_score_threshold), ndocs,
+                                                      k, out_pids_ptr, out_scores_ptr, out_counts_ptr, stream))
+
     def probe(self, Q, nprobe=None):
         """Stage 1: `_topk(Q' * centroids, nprobe, dims = 2)`: (nq, T, nprobe) 1-based centroid ids
         (best first) and their fp32 scores."""

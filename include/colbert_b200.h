@@ -122,6 +122,24 @@ int32_t cb_search_batch_device(cb_index* index, const float* dQ, int32_t nq, int
                                int32_t nprobe, int32_t k, int64_t* d_out_pids,
                                float* d_out_scores, int32_t* d_out_counts, void* stream);
 
+/* PLAID-style pruned search (BASELINE.json config 5).  NOT a reference function: ColBERT.jl lists PLAID
+ * pruning as roadmap (README.md:187); the semantics are defined by oracle/oracle.py `plaid_search`
+ * on top of the reference's own `retrieve` / `decompress` / `maxsim`:
+ *   candidates = `retrieve` with nprobe = ncells (src/search/ranking.jl:23-44); a centroid survives
+ *   for a query iff max_t Q[:,t].c >= centroid_score_threshold; approximate score of a candidate =
+ *   sum_t max(0, max over its tokens with a surviving code of Q[:,t].centroid[code]); the first
+ *   `ndocs` candidates under (approximate score desc, pid asc) get the exact fused
+ *   decompress + MaxSim and the usual stable top-k.
+ * Arguments as cb_search_batch; 1 <= ncells <= 12, 1 <= ndocs <= 1024, 1 <= T <= 32.
+ * out_counts[q] = min(ndocs, #candidates): the number of exactly scored passages. */
+int32_t cb_search_batch_plaid(cb_index* index, const float* Q, int32_t nq, int32_t T, int32_t ncells,
+                              float centroid_score_threshold, int32_t ndocs, int32_t k,
+                              int64_t* out_pids, float* out_scores, int32_t* out_counts);
+int32_t cb_search_batch_plaid_device(cb_index* index, const float* dQ, int32_t nq, int32_t T,
+                                     int32_t ncells, float centroid_score_threshold, int32_t ndocs,
+                                     int32_t k, int64_t* d_out_pids, float* d_out_scores,
+                                     int32_t* d_out_counts, void* stream);
+
 /* ---- stage-level hooks (each mirrors one reference function; host buffers) ---- */
 
 /* Stage 1: `_topk(Q' * centroids, nprobe, dims = 2)` (src/search/ranking.jl:27-31,

@@ -465,6 +465,82 @@ def search(index: Index, Q, k, fast=True):
     return pids[indices][:k], scores[indices][:k]
 
 
+# ---------------------------------------------------------------------------------------------
+# PLAID-style pruned search (BASELINE.json config 5; SURVEY.md section 8c "PLAID knobs", 8f rank f3)
+#
+# The reference has NO implementation of this (README.md:187 lists it as roadmap), so parity is
+# UNPINNED: the semantics below are the ones this oracle defines, following the PLAID paper
+# (Santhanam et al. 2022, stages 1-3) on top of the reference's own retrieve / decompress / maxsim:
+#   1. candidates   = retrieve(...) with nprobe = ncells                      (ranking.jl:23-44)
+#   2. centroid pruning: centroid c survives for the query iff max_t S[t, c] >= threshold, with
+#      S[t, c] the fixed-order fp32 dot of query token t and centroid c (`fixed_order_dot`)
+#   3. approximate score of a candidate = sum over query tokens t of
+#      max(0, max over the passage's tokens e whose code survives of S[t, code_e]);
+#      the sum over the 32 (zero-padded) token maxima is the pairwise tree a warp butterfly forms
+#      (`tree_sum32`), so the value is reproducible bit for bit
+#   4. keep the first `ndocs` candidates under (approximate score desc, pid asc)
+#   5. exact MaxSim (decompress + maxsim) on those, stable descending sort, first k.
+# ---------------------------------------------------------------------------------------------
+def fixed_order_scores(Q, centroids):
+    """S (T, K): S[t, c] = fixed_order_dot(Q[:, t], centroids[:, c])."""
+    Qt = np.ascontiguousarray(np.asarray(Q, dtype=F32).T)          # (T, dim)
+    Ct = np.ascontiguousarray(np.asarray(centroids, dtype=F32).T)  # (K, dim)
+    acc = np.zeros((Qt.shape[0], Ct.shape[0]), dtype=F32)
+    for k in range(Qt.shape[1]):
+        acc = (acc + (Qt[:, k][:, None] * Ct[:, k][None, :]).astype(F32)).astype(F32)
+    return acc
+
+
+def tree_sum32(v):
+    """Sum of 32 fp32 values (last axis, zero-padded to 32) in the order of a warp xor-butterfly:
+    a[i] += a[i ^ 16], then ^8, ^4, ^2, ^1; the result is a[0]."""
+    v = np.asarray(v, dtype=F32)
+    if v.shape[-1] < 32:
+        pad = np.zeros(v.shape[:-1] + (32 - v.shape[-1],), dtype=F32)
+        v = np.concatenate([v, pad], axis=-1)
+    assert v.shape[-1] == 32
+    idx = np.arange(32)
+    a = v.copy()
+    for o in (16, 8, 4, 2, 1):
+        a = (a + a[..., idx ^ o]).astype(F32)
+    return a[..., 0]
+
+
+def plaid_approx_scores(index: "Index", Q, ncells, centroid_score_threshold):
+    """Steps 1-3: (candidate pids ascending, approximate scores in pid order, surviving centroid
+    ids 1-based ascending)."""
+    pids = retrieve(index.ivf, index.ivf_lengths, index.centroids, index.emb2pid, ncells, Q)
+    S = fixed_order_scores(Q, index.centroids)                       # (T, K)
+    keep = S.max(axis=0) >= F32(centroid_score_threshold)            # (K,)
+    Sp = np.where(keep[None, :], np.maximum(S, F32(0)), F32(0)).astype(F32)
+    doclens = np.asarray(index.doclens, dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(doclens)])
+    approx = np.zeros(len(pids), dtype=F32)
+    codes0 = np.asarray(index.codes, dtype=np.int64) - 1
+    for i, pid in enumerate(pids):
+        c = codes0[off[pid - 1]:off[pid]]
+        if len(c) == 0:
+            continue
+        m = Sp[:, c].max(axis=1)                                     # (T,) >= 0
+        approx[i] = tree_sum32(m)
+    return pids, approx, np.nonzero(keep)[0] + 1
+
+
+def plaid_search(index: "Index", Q, k, ncells, centroid_score_threshold, ndocs, return_selected=False):
+    """Steps 1-5.  Returns (pids[:k'], scores[:k']) with k' = min(k, #selected) -- the batched
+    entry point truncates instead of throwing (as `cb_search_batch` does)."""
+    pids, approx, _ = plaid_approx_scores(index, Q, ncells, centroid_score_threshold)
+    order = np.lexsort((pids, -approx.astype(np.float64)))           # approx desc, then pid asc
+    sel = np.sort(pids[order[:ndocs]])
+    codes_packed, residuals_packed = _collect_compressed_embs_for_pids_fast(index.doclens, index.codes, index.residuals, sel)
+    D = decompress(index.dim, index.nbits, index.centroids, index.bucket_weights, codes_packed, residuals_packed, fast=True)
+    scores = maxsim(Q, D, sel, index.doclens) if len(sel) else np.zeros(0, dtype=F32)
+    indices = np.argsort(-scores, kind="stable")
+    kk = min(k, len(sel))
+    out = (sel[indices][:kk], scores[indices][:kk])
+    return out + (sel, pids, approx) if return_selected else out
+
+
 def merge_topk(all_pids, all_scores, k):
     """Checker for the cross-shard merge (no reference counterpart: the reference is single
     device).  all_pids / all_scores (n_lists, nq, k'), empty slots pid 0 / -inf.  Every passage
