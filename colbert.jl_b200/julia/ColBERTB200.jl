@@ -103,6 +103,28 @@ function search_batch(ix::ResidentIndex, Q::Array{Float32, 3}, nprobe::Integer, 
 end
 
 """
+    search_batch_plaid(ix, Q::Array{Float32, 3}, k; ncells = 4, centroid_score_threshold = 0.4f0, ndocs = 1000)
+
+PLAID-style pruned search (the reference's own roadmap item, README.md:187; semantics in
+oracle/oracle.py `plaid_search`): candidates from `ncells` cells per token, centroid-score threshold
+pruning, approximate centroid-only scores, the best `ndocs` re-scored exactly, stable top-k.
+`counts[q]` = number of exactly scored passages.
+"""
+function search_batch_plaid(ix::ResidentIndex, Q::Array{Float32, 3}, k::Integer; ncells::Integer = 4,
+        centroid_score_threshold::Real = 0.4f0, ndocs::Integer = 1000)
+    dim, T, nq = size(Q)
+    pids = zeros(Int64, k, nq)
+    scores = fill(-Inf32, k, nq)
+    counts = zeros(Int32, nq)
+    GC.@preserve Q pids scores counts begin
+        check(ccall((:cb_search_batch_plaid, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float32}, Int32, Int32, Int32, Float32, Int32, Int32, Ptr{Int64}, Ptr{Float32}, Ptr{Int32}),
+            ix.handle, Q, nq, T, ncells, Float32(centroid_score_threshold), ndocs, k, pids, scores, counts))
+    end
+    pids, scores, counts
+end
+
+"""
     search(searcher, query, k)    # drop-in for src/searching.jl:93-128
 
 Same return value and error behaviour as the reference: `(pids[1:k], scores[1:k])`, ties in
