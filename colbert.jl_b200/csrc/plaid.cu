@@ -100,7 +100,7 @@ __global__ void k_plaid_compact_flags(const int32_t* __restrict__ flags, int64_t
 __global__ void __launch_bounds__(128)
 k_plaid_vectors(const float* __restrict__ Q, int T, const float* __restrict__ C, int dim,
                 const unsigned long long* __restrict__ ents, int n, float* __restrict__ vec, int32_t* __restrict__ head,
-                int32_t* __restrict__ next) {
+                int32_t* __restrict__ next, uint32_t* __restrict__ mask) {
   const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (e >= n) return;
@@ -110,7 +110,10 @@ k_plaid_vectors(const float* __restrict__ Q, int T, const float* __restrict__ C,
   float v = 0.f;
   if (lane < T) v = fmaxf(pl_fixed_dot(Q + (q * T + lane) * dim, C + c * dim, dim), 0.f);
   vec[(int64_t)e * 32 + lane] = v;
-  if (lane == 0) next[e] = atomicExch(&head[c], e);
+  if (lane == 0) {
+    next[e] = atomicExch(&head[c], e);
+    atomicOr(&mask[c >> 5], 1u << (c & 31));
+  }
 }
 
 // Approximate scoring, passage-major: one warp per passage.
@@ -119,7 +122,12 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
                const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ head, const int32_t* __restrict__ next,
                const unsigned long long* __restrict__ ents, const float* __restrict__ vec,
                const int64_t* __restrict__ list_off, int32_t* __restrict__ cursors, uint64_t* __restrict__ pairs,
-               int* __restrict__ overflow) {
+               int* __restrict__ overflow, const uint32_t* __restrict__ mask, int mask_words) {
+  // bit c of the mask = centroid c has a survivor list: kept in shared memory when it fits, so that the ~80 % of
+  // tokens whose centroid survives for no query never touch head[] (a random 32-byte L2 sector each)
+  extern __shared__ uint32_t s_mask[];
+  for (int i = threadIdx.x; i < mask_words; i += blockDim.x) s_mask[i] = mask[i];
+  __syncthreads();
   __shared__ uint32_t s_row[8][32];
   __shared__ uint32_t s_hit[8][PL_HCAP];     // entry id of every hit
   __shared__ uint16_t s_hq[8][PL_HCAP];      // its query
@@ -135,7 +143,9 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
     const int64_t e0 = offsets[p];
     const int L = (int)(offsets[p + 1] - e0);
     for (int i = lane; i < L; i += 32) {
-      int32_t h = head[codes[e0 + i]];
+      const int32_t code = codes[e0 + i];
+      if (mask_words > 0 && !((s_mask[code >> 5] >> (code & 31)) & 1u)) continue;
+      int32_t h = head[code];
       while (h >= 0) {
         const uint32_t q = (uint32_t)(ents[h] >> 32);
         if ((s_row[wi][q >> 5] >> (q & 31)) & 1u) {
@@ -165,6 +175,17 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
       }
     }
     __syncwarp();
+  }
+}
+
+// passages with >= 1 selected pair (the rescoring bitmap is sparse: ~1 passage in 9 at C)
+__global__ void __launch_bounds__(256)
+k_plaid_collect_active(const uint32_t* __restrict__ bitmap2, int64_t Np, int W, int32_t* __restrict__ list, int* __restrict__ n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp0; p < Np; p += nwarps) {
+    const uint32_t w = (lane < W) ? bitmap2[p * W + lane] : 0u;
+    if (__any_sync(0xffffffffu, w != 0u) && lane == 0) list[atomicAdd(n, 1)] = (int32_t)p;
   }
 }
 
@@ -286,21 +307,27 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
     CB_TRY(ix->pl_next.ensure(sizeof(int32_t) * (size_t)(n_ents > 0 ? n_ents : 1)));
     CB_TRY(ix->pl_head.ensure(sizeof(int32_t) * (size_t)ix->K));
     CB_CUDA(cudaMemsetAsync(ix->pl_head.p, 0xff, sizeof(int32_t) * (size_t)ix->K, st));
+    const int mask_words_all = (int)((ix->K + 31) / 32);
+    CB_TRY(ix->pl_mask.ensure(sizeof(uint32_t) * (size_t)mask_words_all));
+    CB_CUDA(cudaMemsetAsync(ix->pl_mask.p, 0, sizeof(uint32_t) * (size_t)mask_words_all, st));
     if (n_ents > 0) {
       k_plaid_vectors<<<(unsigned)((n_ents + 3) / 4), 128, 0, st>>>(dQc, T, ix->centroids, ix->dim,
                                                                   ix->pl_ents.as<unsigned long long>(), n_ents,
                                                                   ix->pl_vec.as<float>(), ix->pl_head.as<int32_t>(),
-                                                                  ix->pl_next.as<int32_t>());
+                                                                  ix->pl_next.as<int32_t>(), ix->pl_mask.as<uint32_t>());
       CB_LAUNCH_CHECK();
     }
     CB_TRY(ix->pairs.ensure(sizeof(uint64_t) * (size_t)(total > 0 ? total : 1)));
     if (total > 0 && n_ents > 0 && ix->Np > 0) {
-      const int grid = ix->sm_count * 8;
-      k_plaid_approx<<<grid, 256, 0, st>>>(ix->offsets, ix->Np, ix->codes, W, ix->bitmap.as<uint32_t>(),
+      const int grid = ix->sm_count * 4;
+      const int mask_words = mask_words_all * 4 <= 160 * 1024 ? mask_words_all : 0;   // else: no shared-memory filter
+      const size_t msm = sizeof(uint32_t) * (size_t)mask_words;
+      CB_CUDA(cudaFuncSetAttribute(k_plaid_approx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
+      k_plaid_approx<<<grid, 256, msm, st>>>(ix->offsets, ix->Np, ix->codes, W, ix->bitmap.as<uint32_t>(),
                                            ix->pl_head.as<int32_t>(), ix->pl_next.as<int32_t>(),
                                            ix->pl_ents.as<unsigned long long>(), ix->pl_vec.as<float>(),
                                            ix->list_off.as<int64_t>(), ix->cursors.as<int32_t>(), ix->pairs.as<uint64_t>(),
-                                           d_n_ents + 1);
+                                           d_n_ents + 1, ix->pl_mask.as<uint32_t>(), mask_words);
       CB_LAUNCH_CHECK();
     }
     // 4. first ndocs positives per query (cursors = number of positive pairs), then zero-score fill
@@ -323,8 +350,12 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
       k_plaid_fill<<<n, 1024, 0, st>>>(ix->bitmap.as<uint32_t>(), ix->bitmap2.as<uint32_t>(), ix->Np, W,
                                        ix->pl_npos.as<int32_t>(), ix->pl_sel.as<int32_t>());
       CB_LAUNCH_CHECK();
+      CB_TRY(ix->pl_active.ensure(sizeof(int32_t) * (size_t)ix->Np));
+      k_plaid_collect_active<<<ix->sm_count * 8, 256, 0, st>>>(ix->bitmap2.as<uint32_t>(), ix->Np, W,
+                                                              ix->pl_active.as<int32_t>(), d_n_ents + 2);
+      CB_LAUNCH_CHECK();
     }
-    CB_CUDA(cudaMemcpyAsync(h, d_n_ents + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(h, d_n_ents + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // [0] overflow flag, [1] active passages
     // 5. exact scoring of the selected pairs + final top-k
     CB_TRY(cb_scan_counts(ix->pl_sel.as<int32_t>(), n, ix->list_off.as<int64_t>(), st));
     CB_CUDA(cudaMemsetAsync(ix->cursors.p, 0, sizeof(int32_t) * CB_NQ_CHUNK, st));
@@ -337,9 +368,15 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
     ix->st_plaid_rescored += (double)total2;
     ix->st_pairs = (double)total2;
     CB_TRY(ix->pairs.ensure(sizeof(uint64_t) * (size_t)(total2 > 0 ? total2 : 1)));
-    if (total2 > 0)
-      CB_TRY(cb_stage34_score(ix, dQc, n, T, W, ix->bitmap2.as<uint32_t>(), ix->list_off.as<int64_t>(),
-                              ix->cursors.as<int32_t>(), ix->pairs.as<uint64_t>(), st));
+    if (total2 > 0) {
+      ix->tc_active_list = ix->pl_active.as<int32_t>();   // the tcgen05 kernel visits only these passages
+      ix->tc_active_n = h[1];
+      const int32_t rc = cb_stage34_score(ix, dQc, n, T, W, ix->bitmap2.as<uint32_t>(), ix->list_off.as<int64_t>(),
+                                          ix->cursors.as<int32_t>(), ix->pairs.as<uint64_t>(), st);
+      ix->tc_active_list = nullptr;
+      ix->tc_active_n = 0;
+      CB_TRY(rc);
+    }
     CB_TRY(cb_stage5_topk(ix->pairs.as<uint64_t>(), ix->list_off.as<int64_t>(), n, k, ix->pid_base,
                           d_out_pids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, st));
     CB_CUDA(cudaMemcpyAsync(d_out_counts + q0, ix->pl_sel.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));

@@ -75,6 +75,7 @@ struct TcParams {
   const int64_t* offsets; int64_t Np; int R, W, nastages, ring_bytes, long_limit;
   const uint8_t* qprep;           // query row image: [nq][8 KB]
   const uint32_t* bitmap; const int64_t* list_off; int32_t* cursors; uint64_t* pairs;
+  const int32_t* pid_list; int64_t n_list;   // optional: only these passages (sparse bitmaps, e.g. the PLAID rescoring pass)
 };
 
 // max over 32 / 16 TMEM columns held in registers, folded into 4 independent chains
@@ -252,22 +253,30 @@ k_maxsim_tc(TcParams P) {
     // iterations ahead and carried in registers, so no global latency sits on the per-passage path
     // (one exposed L2/HBM round trip per passage made the scheduler the bottleneck of the kernel at
     // ~17 candidates per passage: nothing downstream ever saw a full pipeline).
-    struct Hdr { int64_t o0, o1, f0, f1; uint32_t w; };
-    auto load_hdr = [&](int64_t p) {
-      Hdr h; h.o0 = h.o1 = h.f0 = h.f1 = 0; h.w = 0u;
-      if (p < P.Np) {
+    struct Hdr { int64_t o0, o1, f0, f1, p; uint32_t w; };
+    // With a passage list (sparse bitmap) item i is passage pid_list[i]: the pid is requested one more
+    // iteration ahead than the header that depends on it.  (No packed-byte prefetch in that mode.)
+    const int64_t n_items = P.pid_list ? P.n_list : P.Np;
+    auto pid_of = [&](int64_t i) -> int64_t { return (P.pid_list && i < n_items) ? (int64_t)P.pid_list[i] : i; };
+    auto load_hdr = [&](int64_t i, int64_t p) {
+      Hdr h; h.o0 = h.o1 = h.f0 = h.f1 = 0; h.w = 0u; h.p = p;
+      if (i < n_items) {
         h.o0 = P.offsets[p]; h.o1 = P.offsets[p + 1];
         h.w = (lane < P.W) ? P.bitmap[p * P.W + lane] : 0u;
         const int64_t pf = p + 6 * stride;       // pull its packed bytes from HBM into L2 a few passages ahead
-        if (pf < P.Np) { h.f0 = P.offsets[pf]; h.f1 = P.offsets[pf + 1]; }
+        if (!P.pid_list && pf < P.Np) { h.f0 = P.offsets[pf]; h.f1 = P.offsets[pf + 1]; }
       }
       return h;
     };
-    Hdr h1 = load_hdr(first), h2 = load_hdr(first + stride);
-    for (int64_t p = first; p < P.Np; p += stride) {
+    Hdr h1 = load_hdr(first, pid_of(first)), h2 = load_hdr(first + stride, pid_of(first + stride));
+    int64_t pq = pid_of(first + 2 * stride);
+    for (int64_t it = first; it < n_items; it += stride) {
       const Hdr h = h1;
       h1 = h2;
-      h2 = load_hdr(p + 2 * stride);
+      const int64_t pq_next = pid_of(it + 3 * stride);
+      h2 = load_hdr(it + 2 * stride, pq);
+      pq = pq_next;
+      const int64_t p = h.p;
       const int64_t e0 = h.o0;
       const int L = (int)(h.o1 - h.o0);
       uint32_t w = h.w;
@@ -650,8 +659,11 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   P.offsets = ix->offsets; P.Np = ix->Np; P.R = ix->R; P.W = W; P.nastages = nast;
   P.ring_bytes = (int)ring; P.long_limit = (int)long_limit;
   P.qprep = ix->q_prep.as<uint8_t>(); P.bitmap = d_bitmap; P.list_off = d_list_off; P.cursors = d_cursors; P.pairs = d_pairs;
+  P.pid_list = ix->tc_active_list; P.n_list = ix->tc_active_n;
+  if (P.pid_list && P.n_list == 0) return CB_OK;
   int64_t grid = ix->sm_count;
-  if (grid > ix->Np) grid = ix->Np;
+  const int64_t n_items = P.pid_list ? P.n_list : ix->Np;
+  if (grid > n_items) grid = n_items;
 #define CB_TC_LAUNCH(NB)                                                                                         \
   do {                                                                                                           \
     CB_CUDA(cudaFuncSetAttribute(k_maxsim_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
