@@ -116,8 +116,10 @@ k_plaid_vectors(const float* __restrict__ Q, int T, const float* __restrict__ C,
   }
 }
 
-// Approximate scoring, passage-major: one warp per passage.
-__global__ void __launch_bounds__(256)
+// Approximate scoring, passage-major: one warp per passage, 16 warps per CTA sharing one copy of the
+// survivor mask, the next passage's bitmap words and extent requested while the current one is processed.
+constexpr int PL_WARPS = 16;
+__global__ void __launch_bounds__(PL_WARPS * 32)
 k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* __restrict__ codes, int W,
                const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ head, const int32_t* __restrict__ next,
                const unsigned long long* __restrict__ ents, const float* __restrict__ vec,
@@ -128,20 +130,25 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
   extern __shared__ uint32_t s_mask[];
   for (int i = threadIdx.x; i < mask_words; i += blockDim.x) s_mask[i] = mask[i];
   __syncthreads();
-  __shared__ uint32_t s_row[8][32];
-  __shared__ uint32_t s_hit[8][PL_HCAP];     // entry id of every hit
-  __shared__ uint16_t s_hq[8][PL_HCAP];      // its query
-  __shared__ int s_n[8];
+  __shared__ uint32_t s_row[PL_WARPS][32];
+  __shared__ uint32_t s_hit[PL_WARPS][PL_HCAP];     // entry id of every hit
+  __shared__ uint16_t s_hq[PL_WARPS][PL_HCAP];      // its query
+  __shared__ int s_n[PL_WARPS];
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * 8 + wi, nwarps = (int64_t)gridDim.x * 8;
+  const int64_t warp0 = (int64_t)blockIdx.x * PL_WARPS + wi, nwarps = (int64_t)gridDim.x * PL_WARPS;
+  uint32_t wn = 0u;
+  int64_t o0n = 0, o1n = 0;
+  if (warp0 < Np) { wn = (lane < W) ? bitmap[warp0 * W + lane] : 0u; o0n = offsets[warp0]; o1n = offsets[warp0 + 1]; }
   for (int64_t p = warp0; p < Np; p += nwarps) {
-    const uint32_t w = (lane < W) ? bitmap[p * W + lane] : 0u;
+    const uint32_t w = wn;
+    const int64_t e0 = o0n;
+    const int L = (int)(o1n - o0n);
+    const int64_t pn = p + nwarps;
+    if (pn < Np) { wn = (lane < W) ? bitmap[pn * W + lane] : 0u; o0n = offsets[pn]; o1n = offsets[pn + 1]; }
     if (!__any_sync(0xffffffffu, w != 0u)) continue;
     s_row[wi][lane] = w;
     if (lane == 0) s_n[wi] = 0;
     __syncwarp();
-    const int64_t e0 = offsets[p];
-    const int L = (int)(offsets[p + 1] - e0);
     for (int i = lane; i < L; i += 32) {
       const int32_t code = codes[e0 + i];
       if (mask_words > 0 && !((s_mask[code >> 5] >> (code & 31)) & 1u)) continue;
@@ -323,7 +330,7 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
       const int mask_words = mask_words_all * 4 <= 160 * 1024 ? mask_words_all : 0;   // else: no shared-memory filter
       const size_t msm = sizeof(uint32_t) * (size_t)mask_words;
       CB_CUDA(cudaFuncSetAttribute(k_plaid_approx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
-      k_plaid_approx<<<grid, 256, msm, st>>>(ix->offsets, ix->Np, ix->codes, W, ix->bitmap.as<uint32_t>(),
+      k_plaid_approx<<<grid, PL_WARPS * 32, msm, st>>>(ix->offsets, ix->Np, ix->codes, W, ix->bitmap.as<uint32_t>(),
                                            ix->pl_head.as<int32_t>(), ix->pl_next.as<int32_t>(),
                                            ix->pl_ents.as<unsigned long long>(), ix->pl_vec.as<float>(),
                                            ix->list_off.as<int64_t>(), ix->cursors.as<int32_t>(), ix->pairs.as<uint64_t>(),
