@@ -133,6 +133,7 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
   __shared__ uint32_t s_row[PL_WARPS][32];
   __shared__ uint32_t s_hit[PL_WARPS][PL_HCAP];     // entry id of every hit
   __shared__ uint16_t s_hq[PL_WARPS][PL_HCAP];      // its query
+  __shared__ uint16_t s_eq[PL_WARPS][PL_HCAP];      // query of every positive score to append
   __shared__ int s_n[PL_WARPS];
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * PL_WARPS + wi, nwarps = (int64_t)gridDim.x * PL_WARPS;
@@ -165,7 +166,10 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
     __syncwarp();
     int nh = s_n[wi];
     if (nh > PL_HCAP) { if (lane == 0) atomicExch(overflow, 1); nh = PL_HCAP; }
-    // fold the hits query by query: hit i leads if no earlier hit has its query
+    // fold the hits query by query: hit i leads if no earlier hit has its query.  The positive scores
+    // are parked in shared memory (slot k <= i of s_hit is dead by then) and appended afterwards with
+    // all the atomics of the passage in flight at once, instead of one dependent round trip per hit.
+    int nemit = 0;
     for (int i = 0; i < nh; i++) {
       const uint32_t q = s_hq[wi][i];
       bool earlier = false;
@@ -176,10 +180,16 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
         if (s_hq[wi][j] == q) m = fmaxf(m, vec[(int64_t)s_hit[wi][j] * 32 + lane]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, o));   // oracle.tree_sum32
-      if (lane == 0 && m > 0.f) {
-        const int pos = atomicAdd(&cursors[q], 1);
-        pairs[list_off[q] + pos] = cb_pair_key(m, (uint32_t)p);
+      if (m > 0.f) {      // warp-uniform: every lane holds the same sum
+        if (lane == 0) { s_hit[wi][nemit] = cb_orderable(m); s_eq[wi][nemit] = (uint16_t)q; }
+        nemit++;
       }
+    }
+    __syncwarp();
+    for (int kx = lane; kx < nemit; kx += 32) {
+      const uint32_t q = s_eq[wi][kx];
+      const int pos = atomicAdd(&cursors[q], 1);
+      pairs[list_off[q] + pos] = ((uint64_t)s_hit[wi][kx] << 32) | (uint64_t)(0xffffffffu - (uint32_t)p);
     }
     __syncwarp();
   }
