@@ -117,7 +117,7 @@ struct cb_index {
   // workspace (grow-only)
   DevBuf q_f32, q_prep, topr_val, topr_idx, cells, cell_scores, flags, bitmap, counts, list_off,
       cursors, pairs, out_pids, out_scores, out_counts, misc, long_list, hook_a, hook_b, hook_c, s1_thr, s1_thr0,
-      bitmap2, pl_ents, pl_misc, pl_vec, pl_next, pl_head, pl_mask, pl_active, pl_top_pids, pl_top_scores, pl_sel, pl_npos;   // PLAID mode (plaid.cu)
+      bitmap_t, bitmap2, pl_ents, pl_misc, pl_vec, pl_next, pl_head, pl_mask, pl_active, pl_top_pids, pl_top_scores, pl_sel, pl_npos;   // PLAID mode (plaid.cu)
   int64_t* pinned_total = nullptr;  // pinned host scalar(s) for the one D2H per batch
   const float* q_prep_src = nullptr; // q_prep currently holds the row image of these query tokens ...
   int64_t q_prep_rows = 0;           // ... (this many rows); reset at the start of every search chunk

@@ -163,7 +163,7 @@ static void destroy_index(cb_index* ix) {
   DevBuf* bufs[] = {&ix->q_f32, &ix->q_prep, &ix->topr_val, &ix->topr_idx, &ix->cells, &ix->cell_scores,
                     &ix->flags, &ix->bitmap, &ix->counts, &ix->list_off, &ix->cursors, &ix->pairs,
                     &ix->out_pids, &ix->out_scores, &ix->out_counts, &ix->misc, &ix->long_list,
-                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0, &ix->bitmap2, &ix->pl_ents, &ix->pl_misc,
+                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0, &ix->bitmap_t, &ix->bitmap2, &ix->pl_ents, &ix->pl_misc,
                     &ix->pl_vec, &ix->pl_next, &ix->pl_head, &ix->pl_mask, &ix->pl_active, &ix->pl_top_pids, &ix->pl_top_scores, &ix->pl_sel, &ix->pl_npos};
   for (DevBuf* b : bufs) b->release();
   if (ix->pinned_total) cudaFreeHost(ix->pinned_total);

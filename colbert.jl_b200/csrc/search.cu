@@ -30,7 +30,7 @@ int32_t cb_candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int np
   ix->q_prep_src = nullptr;
   CB_TRY(cb_stage1_probe(ix, dQ, nrows, nprobe, ix->cells.as<int32_t>(), ix->cell_scores.as<float>(), st));
   if (ix->opt_profile) CB_CUDA(cudaEventRecord(ix->ev[1], st));
-  CB_CUDA(cudaMemsetAsync(ix->bitmap.p, 0, sizeof(uint32_t) * (size_t)ix->Np * W, st));
+  // (the bitmap needs no clearing: stage 2's transpose writes every word of it)
   CB_CUDA(cudaMemsetAsync(ix->counts.p, 0, sizeof(int32_t) * CB_NQ_CHUNK, st));
   CB_CUDA(cudaMemsetAsync(ix->cursors.p, 0, sizeof(int32_t) * CB_NQ_CHUNK, st));
   CB_TRY(cb_stage2_mark(ix, ix->cells.as<int32_t>(), nq, T, nprobe, W, ix->bitmap.as<uint32_t>(),
