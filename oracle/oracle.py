@@ -506,7 +506,7 @@ def tree_sum32(v):
     return a[..., 0]
 
 
-def plaid_approx_scores(index: "Index", Q, ncells, centroid_score_threshold):
+def plaid_approx_scores(index: "Index", Q, ncells, centroid_score_threshold, vectorized=True):
     """Steps 1-3: (candidate pids ascending, approximate scores in pid order, surviving centroid
     ids 1-based ascending)."""
     pids = retrieve(index.ivf, index.ivf_lengths, index.centroids, index.emb2pid, ncells, Q)
@@ -517,12 +517,30 @@ def plaid_approx_scores(index: "Index", Q, ncells, centroid_score_threshold):
     off = np.concatenate([[0], np.cumsum(doclens)])
     approx = np.zeros(len(pids), dtype=F32)
     codes0 = np.asarray(index.codes, dtype=np.int64) - 1
-    for i, pid in enumerate(pids):
-        c = codes0[off[pid - 1]:off[pid]]
-        if len(c) == 0:
+    if not vectorized:                                               # the definition, one candidate at a time
+        for i, pid in enumerate(pids):
+            c = codes0[off[pid - 1]:off[pid]]
+            if len(c) == 0:
+                continue
+            m = Sp[:, c].max(axis=1)                                 # (T,) >= 0
+            approx[i] = tree_sum32(m)
+        return pids, approx, np.nonzero(keep)[0] + 1
+    # same arithmetic, a few thousand candidates at a time (max is exact, the sum order is tree_sum32's)
+    lens = doclens[pids - 1]
+    SpT = np.ascontiguousarray(Sp.T)                                 # (K, T): one row per centroid
+    for a in range(0, len(pids), 4096):
+        sl = slice(a, min(a + 4096, len(pids)))
+        ln = lens[sl]
+        nz = ln > 0
+        if not nz.any():
             continue
-        m = Sp[:, c].max(axis=1)                                     # (T,) >= 0
-        approx[i] = tree_sum32(m)
+        starts = off[pids[sl] - 1]
+        tok = np.concatenate([np.arange(s0, s0 + n) for s0, n in zip(starts[nz], ln[nz])])
+        seg = np.concatenate([[0], np.cumsum(ln[nz])[:-1]])
+        m = np.maximum.reduceat(SpT[codes0[tok]], seg, axis=0)       # (n_nonempty, T)
+        out = np.zeros(len(ln), dtype=F32)
+        out[nz] = tree_sum32(m)
+        approx[sl] = out
     return pids, approx, np.nonzero(keep)[0] + 1
 
 

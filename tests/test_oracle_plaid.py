@@ -63,3 +63,15 @@ def test_plaid_selection_rule():
         # an unreachable threshold: all approximate scores are 0, the selection is the lowest pids
         _, _, sel0, cand0, approx0 = O.plaid_search(oix, Q[q].T, 5, 4, 2.0, 30, return_selected=True)
         assert np.all(approx0 == 0) and np.array_equal(sel0, cand0[:30])
+
+
+def test_plaid_vectorized_equals_definition():
+    ix = S.make_index(1200, 1024, seed=45, doclen_min=0, doclen_mean=20.0, doclen_std=15.0)     # includes empty passages
+    Q = S.make_queries(ix["centroids"], 2, seed=46, nprobe=4)
+    oix = oracle_index(ix)
+    for q in range(2):
+        for thr in (0.3, 0.4):
+            p1, a1, s1 = O.plaid_approx_scores(oix, Q[q].T, 4, thr, vectorized=True)
+            p0, a0, s0 = O.plaid_approx_scores(oix, Q[q].T, 4, thr, vectorized=False)
+            assert np.array_equal(p1, p0) and np.array_equal(s1, s0)
+            assert np.array_equal(a1, a0)          # bit for bit
