@@ -79,18 +79,30 @@ class ShardedSearcher:
         L.check(L.load().cb_merge_topk_device(self.searcher.device, n, nq, k, all_p.data_ptr(), all_s.data_ptr(),
                                               out_p.data_ptr(), out_s.data_ptr(), stream))
 
-    def search_batch_device(self, Qd, k, out_p, out_s, out_c, stream=None, local_p=None, local_s=None):
+    def search_batch_device(self, Qd, k, out_p, out_s, out_c, stream=None, local_p=None, local_s=None, plaid=None):
         """Qd float32 [nq][T][dim] on this rank's GPU (identical on every rank); out_p / out_s
-        [nq][k] receive the GLOBAL first-k on every rank; out_c [nq] the local candidate counts."""
+        [nq][k] receive the GLOBAL first-k on every rank; out_c [nq] the local candidate counts.
+
+        `plaid` = dict(ncells=, centroid_score_threshold=, ndocs=) runs the PLAID-style pruned search
+        (`cb_search_batch_plaid_device`) on every shard instead.  Each shard then keeps ITS first
+        `ndocs` candidates, so the union re-scored exactly is a superset of what one unsharded index
+        would select (never a worse top-k); `out_c` holds the local re-scored counts."""
         import torch
         nq, T, _ = Qd.shape
+
+        def local(p, s_):
+            if plaid is None:
+                self.searcher.search_batch_device(Qd.data_ptr(), nq, T, k, p.data_ptr(), s_.data_ptr(), out_c.data_ptr(),
+                                                  stream=stream)
+            else:
+                self.searcher.search_batch_plaid_device(Qd.data_ptr(), nq, T, k, p.data_ptr(), s_.data_ptr(), out_c.data_ptr(),
+                                                        stream=stream, **plaid)
+
         if self.world == 1:
-            self.searcher.search_batch_device(Qd.data_ptr(), nq, T, k, out_p.data_ptr(), out_s.data_ptr(),
-                                              out_c.data_ptr(), stream=stream)
+            local(out_p, out_s)
             return
         lp = local_p if local_p is not None else torch.empty_like(out_p)
         ls = local_s if local_s is not None else torch.empty_like(out_s)
-        self.searcher.search_batch_device(Qd.data_ptr(), nq, T, k, lp.data_ptr(), ls.data_ptr(), out_c.data_ptr(),
-                                          stream=stream)
+        local(lp, ls)
         all_p, all_s = gather_topk(lp, ls, self.group)
         self.merge(all_p, all_s, out_p, out_s, stream)

@@ -130,3 +130,26 @@ def test_topk_exchange_world2_gloo():
         p.join(timeout=240)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_sharded_searcher_forwards_plaid_options():
+    """world = 1 (no process group): the PLAID knobs reach the shard's `search_batch_plaid_device` unchanged."""
+    import torch
+    calls = []
+
+    class Shard:
+        device = -1
+
+        def search_batch_device(self, *a, **kw):
+            calls.append(("exhaustive", kw))
+
+        def search_batch_plaid_device(self, q_ptr, nq, T, k, p_ptr, s_ptr, c_ptr, **kw):
+            calls.append(("plaid", nq, T, k, kw))
+
+    sh = SH.ShardedSearcher(Shard())
+    Q = torch.zeros((3, 32, 128))
+    out_p, out_s, out_c = torch.zeros((3, 7), dtype=torch.int64), torch.zeros((3, 7)), torch.zeros(3, dtype=torch.int32)
+    sh.search_batch_device(Q, 7, out_p, out_s, out_c)
+    sh.search_batch_device(Q, 7, out_p, out_s, out_c, plaid=dict(ncells=4, centroid_score_threshold=0.4, ndocs=1000))
+    assert calls[0][0] == "exhaustive"
+    assert calls[1] == ("plaid", 3, 32, 7, {"stream": None, "ncells": 4, "centroid_score_threshold": 0.4, "ndocs": 1000})
