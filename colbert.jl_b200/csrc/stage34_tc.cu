@@ -20,10 +20,12 @@
 //     query tokens" is one warp reduction.  Padded token rows duplicate the last real token, so
 //     no column masking is needed.  Passages of 241..480 tokens are two chunks (two accumulators,
 //     one running maximum).
-//   * What bounds it: every (query, passage) pair pulls its 8 KB query tile L2 -> SMEM, and the
-//     chip sustains ~40 B/clk/SM of that (tools/bulk_l2_bw.cu), i.e. >= ~820 clocks per 4-query
-//     group; the MMA of a group is 320-544 clocks and the epilogue less, so the kernel is built to
-//     keep that stream saturated: query tiles 3-4 groups ahead, passages up to 4 ahead.
+//   * What bounds it: every (query, passage) pair pulls its 8 KB query tile L2 -> SM, and the chip
+//     sustains ~8.7 TB/s of that (~34 B/clk/SM; the same rate in eight structurally different
+//     builds of this kernel), i.e. ~950 clocks per 4-query group; the MMA of a
+//     group is 320-544 clocks and every other role has slack, so the kernel is built to keep that
+//     stream saturated: query tiles 3 groups ahead, passages up to 4 ahead, the scheduler's own
+//     global reads two passages ahead.
 //   * Warp-specialised, mbarrier-pipelined: warp 0 = scheduler (candidate lists, ring allocation),
 //     warp 1 = MMA issuer (one thread), warps 2-3 = query-tile loaders, warps 4-7 = epilogue (one
 //     TMEM lane quarter each), warps 8-15 = decompression.  Pipelines: passage entries (4 meta
