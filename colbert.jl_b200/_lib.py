@@ -31,6 +31,7 @@ SIGNATURES = {
     "cb_decompress": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _p, _p, _p, _p, C.c_int64, _p, _p, _p]),
     "cb_maxsim": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int64, _p, C.c_int64, _p, C.c_int64, _p]),
     "cb_score_pids": (C.c_int32, [_p, _p, C.c_int32, _p, C.c_int64, _p]),
+    "cb_debug_tc_operand": (C.c_int32, [_p, _p, C.c_int64, _p, _p, C.c_int64]),
     "cb_merge_topk": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "cb_merge_topk_device": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p, _p]),
 }

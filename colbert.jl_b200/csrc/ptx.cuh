@@ -32,19 +32,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hang.
-// `backoff_ns` > 0 makes a waiting warp sleep between polls so that roles with slack (e.g. the
+// Wait for a phase of an mbarrier.  `mbarrier.try_wait` suspends the thread in hardware for a
+// system-dependent time before it reports failure, so the loop is not a busy spin; `backoff_ns` > 0
+// additionally makes a waiting warp sleep between polls so that roles with slack (e.g. the
 // decompression warps) do not steal issue slots from the warps on the critical path.
+// Release builds never give up: a legitimate wait can be arbitrarily long under time-slicing, MPS,
+// a debugger or profiler replay, and a trap would take the caller's whole CUDA context with it.
+// Build with -DCB_DEBUG_WAIT to turn a pipeline bug into a trapped kernel with a message instead
+// of a hang (the printf makes every value live across the wait a spill: debug builds only).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, unsigned backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
+#ifdef CB_DEBUG_WAIT
   const long long t0 = clock64();
+#endif
   while (!mbar_try_wait(bar, parity)) {
     if (backoff_ns) __nanosleep(backoff_ns);
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+#ifdef CB_DEBUG_WAIT
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
       printf("colbert_b200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
              threadIdx.x, parity);
       __trap();
     }
+#else
+    (void)tag;
+#endif
   }
 }
 

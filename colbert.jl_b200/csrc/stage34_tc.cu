@@ -49,9 +49,13 @@ constexpr int TC_MAX_ASTAGES = 6;
 constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots == tile barriers)
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
 constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
-constexpr int TC_NDEC_WARPS = 8;
+#ifndef TC_NLOAD
+#define TC_NLOAD 2                     // query-tile loader warps (2: warps 2-3; 4: two more taken from the decompression pool)
+#endif
+constexpr int TC_NDEC_WARPS = 8 - (TC_NLOAD - 2);
+constexpr int TC_DEC_FIRST = TC_DEC_WARP0 + (TC_NLOAD - 2);   // first decompression warp (loaders 2.. sit before it)
 constexpr int TC_NTEAMS = 2;            // decompression teams (alternate passages)
-constexpr int TC_THREADS = 32 * (TC_DEC_WARP0 + TC_NDEC_WARPS);
+constexpr int TC_THREADS = 32 * (TC_DEC_FIRST + TC_NDEC_WARPS);
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 256;
 
 struct Meta {            // one passage entry, written by the scheduler
@@ -102,18 +106,20 @@ __device__ __forceinline__ void fold16(const uint32_t (&r)[16], float& m0, float
 }
 
 // Decompression helpers.  EIGHT lanes expand one token (a warp expands 4 tokens at a time): lane l8
-// owns dims 16*l8 .. 16*l8+15 = two adjacent 16-byte chunks of the fp16 operand row.  Its 16*NBITS
-// packed bits ...
-template <int NBITS> struct Bits16;
-template <> struct Bits16<1> { uint32_t v; };        // 2 bytes
-template <> struct Bits16<2> { uint32_t v; };        // 4 bytes
-template <> struct Bits16<4> { uint2 v; };           // 8 bytes
+// owns dims 8*l8 .. 8*l8+7 and 64+8*l8 .. 64+8*l8+7, i.e. 16-byte chunk l8 of BOTH 64-element
+// K-blocks of the fp16 operand row.  With that split (a) each of the lane's two 16-byte stores is,
+// across the 8 lanes of a token, one whole 128-byte swizzled row of one K-block: the quarter-warp
+// that shared memory serves per wavefront covers all 32 banks (the earlier "two adjacent chunks per
+// lane" split put lanes l8 and l8+4 on the same banks: 2.5 G excess store wavefronts per batch,
+// ncu), and (b) each of its two 16-byte centroid loads is, across the 8 lanes, one whole 128-byte
+// line (half-used lines before: twice the L1 wavefronts per token).  Its 2 x 8*NBITS packed bits ...
+template <int NBITS> struct Bits16 { uint32_t lo, hi; };   // NBITS bytes each: dims 8*l8.. and 64+8*l8..
 template <int NBITS>
 __device__ __forceinline__ Bits16<NBITS> load_bits16(const uint8_t* __restrict__ emb, int l8) {
   Bits16<NBITS> b;
-  if constexpr (NBITS == 1) b.v = reinterpret_cast<const uint16_t*>(emb)[l8];
-  else if constexpr (NBITS == 2) b.v = reinterpret_cast<const uint32_t*>(emb)[l8];
-  else b.v = reinterpret_cast<const uint2*>(emb)[l8];
+  if constexpr (NBITS == 1) { b.lo = emb[l8]; b.hi = emb[8 + l8]; }
+  else if constexpr (NBITS == 2) { b.lo = reinterpret_cast<const uint16_t*>(emb)[l8]; b.hi = reinterpret_cast<const uint16_t*>(emb)[8 + l8]; }
+  else { b.lo = reinterpret_cast<const uint32_t*>(emb)[l8]; b.hi = reinterpret_cast<const uint32_t*>(emb)[8 + l8]; }
   return b;
 }
 // ... are expanded through a shared-memory table indexed by packed BYTE: entry = the 8/NBITS bucket
@@ -129,26 +135,26 @@ template <int NBITS> struct LutGeom {
 constexpr int TC_LUT_BYTES = 256 * 128;
 template <int NBITS>
 __device__ __forceinline__ void lookup_weights16(const uint8_t* __restrict__ lut_lane, const Bits16<NBITS>& b, __half2 (&w)[8]) {
-  // lut_lane = table + (lane % replicas) * entry_bytes
-  if constexpr (NBITS == 1) {
+  // lut_lane = table + (lane % replicas) * entry_bytes; w[0..3] = dims 8*l8.., w[4..7] = dims 64+8*l8..
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const uint4 x = *reinterpret_cast<const uint4*>(lut_lane + ((b.v >> (8 * j)) & 255u) * 128u);
-      w[4 * j] = *reinterpret_cast<const __half2*>(&x.x); w[4 * j + 1] = *reinterpret_cast<const __half2*>(&x.y);
-      w[4 * j + 2] = *reinterpret_cast<const __half2*>(&x.z); w[4 * j + 3] = *reinterpret_cast<const __half2*>(&x.w);
-    }
-  } else if constexpr (NBITS == 2) {
+  for (int h = 0; h < 2; h++) {
+    const uint32_t bits = h ? b.hi : b.lo;
+    if constexpr (NBITS == 1) {
+      const uint4 x = *reinterpret_cast<const uint4*>(lut_lane + (bits & 255u) * 128u);
+      w[4 * h] = *reinterpret_cast<const __half2*>(&x.x); w[4 * h + 1] = *reinterpret_cast<const __half2*>(&x.y);
+      w[4 * h + 2] = *reinterpret_cast<const __half2*>(&x.z); w[4 * h + 3] = *reinterpret_cast<const __half2*>(&x.w);
+    } else if constexpr (NBITS == 2) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint2 x = *reinterpret_cast<const uint2*>(lut_lane + ((b.v >> (8 * j)) & 255u) * 128u);
-      w[2 * j] = *reinterpret_cast<const __half2*>(&x.x); w[2 * j + 1] = *reinterpret_cast<const __half2*>(&x.y);
-    }
-  } else {
+      for (int j = 0; j < 2; j++) {
+        const uint2 x = *reinterpret_cast<const uint2*>(lut_lane + ((bits >> (8 * j)) & 255u) * 128u);
+        w[4 * h + 2 * j] = *reinterpret_cast<const __half2*>(&x.x); w[4 * h + 2 * j + 1] = *reinterpret_cast<const __half2*>(&x.y);
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t word = j < 4 ? b.v.x : b.v.y;
-      const uint32_t x = *reinterpret_cast<const uint32_t*>(lut_lane + ((word >> (8 * (j & 3))) & 255u) * 128u);
-      w[j] = *reinterpret_cast<const __half2*>(&x);
+      for (int j = 0; j < 4; j++) {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(lut_lane + ((bits >> (8 * j)) & 255u) * 128u);
+        w[4 * h + j] = *reinterpret_cast<const __half2*>(&x);
+      }
     }
   }
 }
@@ -160,15 +166,27 @@ __device__ __forceinline__ void lookup_weights16(const uint8_t* __restrict__ lut
 // and the 8-lane group; the scale is applied as v*hi + v*lo with (hi, lo) the fp16 split of the
 // fp32 1/(|v|+eps), so no systematic per-token scale error survives.  Measured score error against
 // the fp32 oracle stays below 2e-4 relative (tolerance 1e-3, tests/test_gpu_parity.py).
-template <int NBITS>
+// DUMP (parity hook only, cb_debug_tc_operand): additionally writes the un-normalised fp16 sums of this lane
+// to raw_row[dims] -- fp16(centroid) + fp16(w[bucket]) is exactly reproducible on the host, which pins
+// every unpacked bucket index of THIS code path bit for bit.
+template <int NBITS, bool DUMP = false>
 __device__ __forceinline__ void finish_token16(const uint8_t* __restrict__ lut_lane, const Bits16<NBITS>& bits, const uint4 (&craw)[2],
-                                               int l8, uint8_t* tile, int kb_stride, int row) {
+                                               int l8, uint8_t* tile, int kb_stride, int row, __half* raw_row = nullptr) {
   __half2 v[8];
   lookup_weights16<NBITS>(lut_lane, bits, v);
   const __half2* c0 = reinterpret_cast<const __half2*>(&craw[0]);
   const __half2* c1 = reinterpret_cast<const __half2*>(&craw[1]);
 #pragma unroll
   for (int j = 0; j < 4; j++) { v[j] = __hadd2(c0[j], v[j]); v[4 + j] = __hadd2(c1[j], v[4 + j]); }
+  if constexpr (DUMP) {
+    if (raw_row != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        reinterpret_cast<__half2*>(raw_row + 8 * l8)[j] = v[j];
+        reinterpret_cast<__half2*>(raw_row + 64 + 8 * l8)[j] = v[4 + j];
+      }
+    }
+  }
   __half2 s0 = __hmul2(v[0], v[0]), s1 = __hmul2(v[1], v[1]), s2 = __hmul2(v[2], v[2]), s3 = __hmul2(v[3], v[3]);
   s0 = __hfma2(v[4], v[4], s0); s1 = __hfma2(v[5], v[5], s1); s2 = __hfma2(v[6], v[6], s2); s3 = __hfma2(v[7], v[7], s3);
   const float2 f0 = __half22float2(s0), f1 = __half22float2(s1), f2 = __half22float2(s2), f3 = __half22float2(s3);
@@ -179,17 +197,93 @@ __device__ __forceinline__ void finish_token16(const uint8_t* __restrict__ lut_l
   const __half hi = __float2half_rn(inv);
   const __half lo = __float2half_rn(inv - __half2float(hi));
   const __half2 hi2 = __half2half2(hi), lo2 = __half2half2(lo);
-  uint8_t* base = tile + (l8 >> 2) * kb_stride + (row >> 3) * 1024 + (row & 7) * 128;
+  uint8_t* base = tile + (row >> 3) * 1024 + (row & 7) * 128 + ((l8 ^ (row & 7)) << 4);   // SWIZZLE_128B: chunk c of row r sits at c ^ (r & 7)
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
+  for (int h = 0; h < 2; h++) {     // h = K-block
     uint4 o;
     __half2 t;
     t = __hfma2(v[4 * h + 0], lo2, __hmul2(v[4 * h + 0], hi2)); o.x = *reinterpret_cast<const uint32_t*>(&t);
     t = __hfma2(v[4 * h + 1], lo2, __hmul2(v[4 * h + 1], hi2)); o.y = *reinterpret_cast<const uint32_t*>(&t);
     t = __hfma2(v[4 * h + 2], lo2, __hmul2(v[4 * h + 2], hi2)); o.z = *reinterpret_cast<const uint32_t*>(&t);
     t = __hfma2(v[4 * h + 3], lo2, __hmul2(v[4 * h + 3], hi2)); o.w = *reinterpret_cast<const uint32_t*>(&t);
-    const int chunk = ((2 * l8 + h) & 7) ^ (row & 7);      // SWIZZLE_128B: 16-byte chunk c of row r sits at c ^ (r & 7)
-    *reinterpret_cast<uint4*>(base + (chunk << 4)) = o;
+    *reinterpret_cast<uint4*>(base + h * kb_stride) = o;
+  }
+}
+
+// Operand-tile geometry of a passage of L tokens: one chunk of n0 rows (L padded to 16), or two
+// balanced chunks when L > TC_MAX_BROWS (two accumulators, one running maximum).
+__device__ __forceinline__ void tc_tile_geometry(int L, int& nchunk, int& n0, int& n1) {
+  nchunk = 1; n0 = (L + 15) & ~15; n1 = 0;
+  if (L > TC_MAX_BROWS) {
+    nchunk = 2;
+    n0 = (((L + 1) >> 1) + 15) & ~15;
+    n1 = (L - n0 + 15) & ~15;
+  }
+}
+
+// byte -> bucket weights table (fp16, every entry replicated across its 128-byte bank row)
+template <int NBITS>
+__device__ __forceinline__ void tc_fill_lut(uint8_t* s_lut, const float* __restrict__ weights, int tid, int nthreads) {
+  constexpr int DPB = 8 / NBITS, REP = LutGeom<NBITS>::REPLICAS;
+  for (int i = tid; i < 256 * REP * DPB; i += nthreads) {
+    const int j = i % DPB, r = (i / DPB) % REP, byte = i / (DPB * REP);
+    reinterpret_cast<__half*>(s_lut + byte * 128 + r * LutGeom<NBITS>::ENTRY_BYTES)[j] =
+        __float2half_rn(weights[(byte >> (j * NBITS)) & ((1 << NBITS) - 1)]);
+  }
+}
+
+constexpr int TC_DBATCH = 5;
+constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
+
+// One team warp's share of a passage: packed codes/residuals -> normalised fp16 operand tile(s) in shared
+// memory (rows past the last token re-expand the last token).  Used by the scoring kernel's
+// decompression role and, unchanged, by the parity hook kernel k_tc_dump (DUMP = true).
+template <int NBITS, bool DUMP>
+__device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const uint8_t* __restrict__ lut_lane, int dw, int lane,
+                                                      int L, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out) {
+  constexpr int TEAM_WARPS = TC_TEAM_WARPS;
+  const int l8 = lane & 7;
+  uint8_t* tile1 = tile0 + n0 * 256;
+  const int nrows = n0 + n1;                                    // operand rows (multiple of 16)
+  // operand row of this lane in round j: rr = 4 * (dw + TEAM_WARPS * j) + (lane >> 3)
+  const int rr0 = 4 * dw + (lane >> 3);
+  const int nround = (nrows - 4 * dw + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);   // warp-uniform
+  const int nround_max = (nrows + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);
+  const int nbatch = (nround_max + TC_DBATCH - 1) / TC_DBATCH;
+  const int per = (nround_max + nbatch - 1) / nbatch;           // balanced batch length (<= TC_DBATCH)
+  int32_t code_next[TC_DBATCH];
+#pragma unroll
+  for (int i = 0; i < TC_DBATCH; i++) {
+    const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
+    code_next[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
+  }
+  for (int j0 = 0; j0 < nround; j0 += per) {
+    Bits16<NBITS> bits[TC_DBATCH];
+    uint4 cr[TC_DBATCH][2];
+#pragma unroll
+    for (int i = 0; i < TC_DBATCH; i++) {
+      if (i < per && j0 + i < nround) {
+        const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + i), L - 1);
+        bits[i] = load_bits16<NBITS>(P.residuals + (e0 + t) * P.R, l8);
+        const uint4* crow = reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM) + l8;
+        cr[i][0] = crow[0];
+        cr[i][1] = crow[8];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TC_DBATCH; i++) {
+      const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + per + i), L - 1);
+      code_next[i] = (i < per && j0 + per + i < nround) ? P.codes[e0 + t] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < TC_DBATCH; i++) {
+      if (i < per && j0 + i < nround) {   // warp-uniform
+        const int rr = rr0 + 4 * TEAM_WARPS * (j0 + i);
+        const int c = rr >= n0 ? 1 : 0;
+        finish_token16<NBITS, DUMP>(lut_lane, bits[i], cr[i], l8, c ? tile1 : tile0, (c ? n1 : n0) * 128, rr - c * n0,
+                                    (DUMP && rr < L) ? raw_out + (size_t)rr * TC_DIM : nullptr);
+      }
+    }
   }
 }
 
@@ -217,28 +311,59 @@ k_maxsim_tc(TcParams P) {
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
       ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], 1);
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], 2 + TC_NEPI_WARPS);
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS);
     }
     for (int i = 0; i < 2; i++) {
       for (int s = 0; s < TC_EPI_SETS; s++) ptx::mbar_init(&bar->d_full[s][i], 1);
       ptx::mbar_init(&bar->d_empty[i], 4);
     }
-    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], 1); ptx::mbar_init(&bar->a_empty[i], 1); }
+    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], 1); }
     ptx::fence_barrier_init();
   }
-  {  // byte -> bucket weights table (fp16, every entry replicated across its 128-byte bank row)
-    constexpr int DPB = 8 / NBITS, REP = LutGeom<NBITS>::REPLICAS;
-    for (int i = tid; i < 256 * REP * DPB; i += TC_THREADS) {
-      const int j = i % DPB, r = (i / DPB) % REP, byte = i / (DPB * REP);
-      reinterpret_cast<__half*>(s_lut + byte * 128 + r * LutGeom<NBITS>::ENTRY_BYTES)[j] =
-          __float2half_rn(P.weights[(byte >> (j * NBITS)) & ((1 << NBITS) - 1)]);
-    }
-  }
+  tc_fill_lut<NBITS>(s_lut, P.weights, tid, TC_THREADS);
   if (warp == 1) ptx::tmem_alloc(s_tmem, TC_TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+
+  // ===== query-tile loaders: EVERY loader serves EVERY group, loader li fetching the group's queries
+  // j = li, li + TC_NLOAD, ...  One warp sustains only ~31 B/clk of 8 KB bulk copies (a copy occupies
+  // its issuing warp for ~270 clocks: tools/l2_to_sm_ceiling.cu, profiles/r02_l2_to_sm_ceiling.txt),
+  // while the L2 -> SM path itself carries 76 B/clk/SM; spreading one group's four copies over
+  // several issuers shortens the fill time of a stage, which is what paces the 3-stage ring. =====
+  auto loader_role = [&](const int li) {
+    uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 8);
+      const Meta& m = meta[slot];
+      const int ncand = m.ncand;
+      if (ncand < 0) break;
+      const int ngroups = (ncand + 3) >> 2;
+      for (int g = 0; g < ngroups; g++) {
+        const uint32_t st_g = st, par_g = a_par;
+        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
+        ptx::mbar_wait(&bar->a_empty[st_g], par_g, 9);
+        const int nqg = min(4, ncand - g * 4);
+        uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
+        const int nmine = (nqg - li + TC_NLOAD - 1) / TC_NLOAD;      // queries li, li + TC_NLOAD, ... < nqg
+        if (nmine <= 0) {
+          if (ptx::elect_one()) ptx::mbar_arrive(&bar->a_full[st_g]);
+          continue;
+        }
+        const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * TC_NLOAD] : 0;   // lane i holds this loader's i-th query
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nmine * TC_Q_BYTES);
+        for (int i = 0; i < nmine; i++) {
+          const int q = __shfl_sync(0xffffffffu, qv, i);
+          if (ptx::elect_one())
+            ptx::bulk_g2s(dst + (li + i * TC_NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
+    }
+  };
 
   // Register budget per warpgroup (setmaxnreg sits at the top of each role's branch so ptxas
   // allocates per role): the epilogue keeps two TMEM load batches in flight, the rest need little.
@@ -292,12 +417,8 @@ k_maxsim_tc(TcParams P) {
       if (L <= 0 || L > P.long_limit) w = 0u;          // empty, or too long: the generic kernel scores it
       if (!__any_sync(0xffffffffu, w != 0u)) continue;  // no query of the batch wants this passage
       // tile geometry
-      int nchunk = 1, n0 = (L + 15) & ~15, n1 = 0;
-      if (L > TC_MAX_BROWS) {
-        nchunk = 2;
-        n0 = (((L + 1) >> 1) + 15) & ~15;
-        n1 = (L - n0 + 15) & ~15;
-      }
+      int nchunk, n0, n1;
+      tc_tile_geometry(L, nchunk, n0, n1);
       const uint32_t bytes = (uint32_t)(n0 + n1) * 256u;
       // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
       const int slot = e & (TC_NSLOT - 1);
@@ -396,33 +517,7 @@ k_maxsim_tc(TcParams P) {
     }
     __syncwarp();
   } else {
-    // ===== query-tile loaders (warps 2, 3: group u belongs to loader u & 1) =====
-    const int li = warp - 2;
-    uint32_t ua = 0, st = 0, a_par = 1;   // stage of group ua / parity of its next a_empty phase
-    for (int e = 0;; e++) {
-      const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 8);
-      const Meta& m = meta[slot];
-      const int ncand = m.ncand;
-      if (ncand < 0) break;
-      const int ngroups = (ncand + 3) >> 2;
-      for (int g = 0; g < ngroups; g++, ua++) {
-        const uint32_t st_g = st, par_g = a_par;
-        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
-        if ((int)(ua & 1) != li) continue;
-        ptx::mbar_wait(&bar->a_empty[st_g], par_g, 9);
-        const int nqg = min(4, ncand - g * 4);
-        uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
-        const int qv = (lane < nqg) ? (int)m.q[g * 4 + lane] : 0;   // lane j holds query j of the group
-        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nqg * TC_Q_BYTES);
-        for (int j = 0; j < nqg; j++) {
-          const int q = __shfl_sync(0xffffffffu, qv, j);
-          if (ptx::elect_one()) ptx::bulk_g2s(dst + j * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
-    }
+    loader_role(warp - 2);
   }
   } else if (warp < TC_DEC_WARP0) {
     if constexpr (TC_EPI_SETS == 1) ptx::reg_inc<176>();
@@ -511,12 +606,15 @@ k_maxsim_tc(TcParams P) {
           if (ncol & 16) fold16(rt, m0, m1, m2, m3);
         }
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        // sum over the 32 query tokens: exact integer warp reduction of 2^-23 fixed point
-        // (|mx| <= ~1, 32 terms: no overflow; resolution 1.2e-7, far inside the 1e-3 tolerance)
-        const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 8388608.0f));
+        // sum over the 32 query tokens: exact (order-free) integer warp reduction of 2^-18 fixed point.
+        // Range: the operand rows are unit vectors, so |mx| <= |q token|; the 32-term sum cannot
+        // overflow while every |q token| <= 255 (cb_tc_prep_rows flags a batch that breaks this and the
+        // batch is scored by the generic fp32 kernel instead).  Resolution 3.8e-6 per token: <= 6.1e-5
+        // absolute on a score, far inside the 1e-3 relative tolerance.
+        const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 262144.0f));
         const int qi = g * 4 + q4;
         if (qi < ncand) {
-          const float score = (float)isum * (1.0f / 8388608.0f);
+          const float score = (float)isum * (1.0f / 262144.0f);
           if (lane == (cnt & 31)) {
             my_q = m.q[qi];
             my_key = ((uint64_t)cb_orderable(score) << 32) | pid_inv;
@@ -531,6 +629,9 @@ k_maxsim_tc(TcParams P) {
     flush();
   } else {
     if constexpr (TC_EPI_SETS == 1) ptx::reg_dec<112>();
+    if (warp < TC_DEC_FIRST) {
+      loader_role(warp - TC_DEC_WARP0 + 2);
+    } else {
     // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
     // Eight lanes per token, four tokens per warp-round (fewer, wider instructions per token than a
     // finer split).  What matters besides instruction count is memory-level parallelism (code ->
@@ -539,68 +640,28 @@ k_maxsim_tc(TcParams P) {
     // passage in balanced batches of up to TC_DBATCH rounds with every load of a batch issued
     // before any of it is consumed and the codes of the next batch already requested.  Operand
     // rows past the last token (padding to 16) re-expand the last token: no column masking later.
-    constexpr int TC_DBATCH = 5;
-    constexpr int TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
-    const int team = (warp - TC_DEC_WARP0) / TEAM_WARPS, dw = (warp - TC_DEC_WARP0) % TEAM_WARPS, l8 = lane & 7;
+    const int team = (warp - TC_DEC_FIRST) / TC_TEAM_WARPS, dw = (warp - TC_DEC_FIRST) % TC_TEAM_WARPS;
     const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
     for (int e = team;; e += TC_NTEAMS) {
-      // an entry of another team between this team's previous entry and e may end the stream
+      // An entry of another team between this team's previous entry and e may end the stream.  Every
+      // decompression warp looks at EVERY entry exactly once and is one of the arrivals that release
+      // its meta slot, so the scheduler cannot republish a slot (and flip the parity this probe waits
+      // on) before the probe has happened.
       bool stop = false;
       for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
         const int sl = ee & (TC_NSLOT - 1);
         ptx::mbar_wait(&bar->meta_full[sl], (ee >> 2) & 1, 12, 20);
         if (meta[sl].ncand < 0) { stop = true; break; }
+        if (ee != e) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[sl]); }
       }
       if (stop) break;
       const int slot = e & (TC_NSLOT - 1);
       const Meta& m = meta[slot];
-      const int L = m.L, n0 = m.n0, n1 = m.n1;
-      const int64_t e0 = m.e0;
-      uint8_t* tile0 = ring + m.b_off;
-      uint8_t* tile1 = tile0 + n0 * 256;
-      const int nrows = n0 + n1;                                    // operand rows (multiple of 16)
-      // operand row of this lane in round j: rr = 4 * (dw + TEAM_WARPS * j) + (lane >> 3)
-      const int rr0 = 4 * dw + (lane >> 3);
-      const int nround = (nrows - 4 * dw + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);   // warp-uniform
-      const int nround_max = (nrows + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);
-      const int nbatch = (nround_max + TC_DBATCH - 1) / TC_DBATCH;
-      const int per = (nround_max + nbatch - 1) / nbatch;           // balanced batch length (<= TC_DBATCH)
-      int32_t code_next[TC_DBATCH];
-#pragma unroll
-      for (int i = 0; i < TC_DBATCH; i++) {
-        const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
-        code_next[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
-      }
-      for (int j0 = 0; j0 < nround; j0 += per) {
-        Bits16<NBITS> bits[TC_DBATCH];
-        uint4 cr[TC_DBATCH][2];
-#pragma unroll
-        for (int i = 0; i < TC_DBATCH; i++) {
-          if (i < per && j0 + i < nround) {
-            const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + i), L - 1);
-            bits[i] = load_bits16<NBITS>(P.residuals + (e0 + t) * P.R, l8);
-            const uint4* crow = reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM) + 2 * l8;
-            cr[i][0] = crow[0];
-            cr[i][1] = crow[1];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < TC_DBATCH; i++) {
-          const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + per + i), L - 1);
-          code_next[i] = (i < per && j0 + per + i < nround) ? P.codes[e0 + t] : 0;
-        }
-#pragma unroll
-        for (int i = 0; i < TC_DBATCH; i++) {
-          if (i < per && j0 + i < nround) {   // warp-uniform
-            const int rr = rr0 + 4 * TEAM_WARPS * (j0 + i);
-            const int c = rr >= n0 ? 1 : 0;
-            finish_token16<NBITS>(lut_lane, bits[i], cr[i], l8, c ? tile1 : tile0, (c ? n1 : n0) * 128, rr - c * n0);
-          }
-        }
-      }
+      tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->b_full[slot]);
+      if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
+    }
     }
   }
 
@@ -609,6 +670,41 @@ k_maxsim_tc(TcParams P) {
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+
+// Parity hook (cb_debug_tc_operand): the decompression of the scoring kernel -- the SAME device functions,
+// one team of TC_TEAM_WARPS warps per listed passage -- with the operand tile copied out un-swizzled.
+// out_norm / out_raw: fp16 [sum of doclens][128]; passages the tcgen05 kernel does not take (empty, or longer
+// than long_limit) leave their rows untouched.
+template <int NBITS>
+__global__ void __launch_bounds__(32 * TC_TEAM_WARPS)
+k_tc_dump(TcParams P, const int32_t* __restrict__ pids, const int64_t* __restrict__ out_off, __half* __restrict__ out_norm,
+          __half* __restrict__ out_raw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* tile0 = smem;                                   // up to 2 * TC_MAX_BROWS + 32 rows
+  uint8_t* s_lut = smem + (2 * TC_MAX_BROWS + 32) * 256;
+  const int tid = threadIdx.x, dw = tid >> 5, lane = tid & 31;
+  tc_fill_lut<NBITS>(s_lut, P.weights, tid, 32 * TC_TEAM_WARPS);
+  __syncthreads();
+  const int64_t p = pids[blockIdx.x];
+  const int64_t e0 = P.offsets[p];
+  const int L = (int)(P.offsets[p + 1] - e0);
+  if (L <= 0 || L > P.long_limit) return;
+  int nchunk, n0, n1;
+  tc_tile_geometry(L, nchunk, n0, n1);
+  const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
+  tc_decompress_passage<NBITS, true>(P, lut_lane, dw, lane, L, n0, n1, e0, tile0, out_raw + out_off[blockIdx.x] * TC_DIM);
+  __syncthreads();
+  // row rr of chunk c, 16-byte chunk j (K-block j >> 3): the inverse of the address finish_token16 wrote
+  for (int i = tid; i < L * 16; i += 32 * TC_TEAM_WARPS) {
+    const int rr = i >> 4, j = i & 15;
+    const int c = rr >= n0 ? 1 : 0, row = rr - c * n0;
+    const uint8_t* t = (c ? tile0 + n0 * 256 : tile0) + (j >> 3) * ((c ? n1 : n0) * 128);
+    const uint4 v = *reinterpret_cast<const uint4*>(t + (row >> 3) * 1024 + (row & 7) * 128 + (((j & 7) ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(out_norm + (out_off[blockIdx.x] + rr) * TC_DIM + j * 8) = v;
   }
 }
 
@@ -696,5 +792,72 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
       CB_TRY(cb_stage34_generic(ix, dQ, nq, T, W, d_bitmap, ix->long_list.as<int32_t>() + 1, ix->n_long, d_list_off,
                                 d_cursors, d_pairs, st));
   }
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity hook: what the tcgen05 kernel's decompression writes into its operand tiles
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tc_dump_lens(const int64_t* __restrict__ pids, int64_t n, int64_t pid_base, int64_t Np, const int64_t* __restrict__ offsets,
+                               int32_t* __restrict__ local, int64_t* __restrict__ lens) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = pids[i] - 1 - pid_base;
+  if (p < 0 || p >= Np) { local[i] = 0; lens[i] = -1; return; }
+  local[i] = (int32_t)p;
+  lens[i] = offsets[p + 1] - offsets[p];
+}
+
+extern "C" int32_t cb_debug_tc_operand(cb_index* ix, const int64_t* pids, int64_t n_pids, uint16_t* out_norm, uint16_t* out_raw,
+                                       int64_t capacity_rows) {
+  CB_REQUIRE(ix != nullptr, CB_ERR_BAD_ARG, "index handle is NULL");
+  CB_REQUIRE(cb_stage34_tc_supported(ix, TC_T), CB_ERR_UNSUPPORTED, "the tcgen05 scoring kernel does not take this index (dim / nbits)");
+  CB_REQUIRE(n_pids >= 0 && (n_pids == 0 || (pids && out_norm && out_raw)), CB_ERR_BAD_ARG, "bad argument");
+  if (n_pids == 0) return CB_OK;
+  CB_CUDA(cudaSetDevice(ix->device));
+  int64_t *d_pids = nullptr;
+  CB_CUDA(cudaMalloc((void**)&d_pids, (size_t)n_pids * (8 + 8 + 8 + 4) + 64));
+  struct G { void* p; ~G() { cudaFree(p); } } g{d_pids};
+  int64_t* d_lens = d_pids + n_pids;
+  int64_t* d_off = d_lens + n_pids;
+  int32_t* d_local = reinterpret_cast<int32_t*>(d_off + n_pids);
+  CB_CUDA(cudaMemcpy(d_pids, pids, sizeof(int64_t) * n_pids, cudaMemcpyHostToDevice));
+  k_tc_dump_lens<<<(unsigned)((n_pids + 255) / 256), 256>>>(d_pids, n_pids, ix->pid_base, ix->Np, ix->offsets, d_local, d_lens);
+  CB_LAUNCH_CHECK();
+  std::string lens_h((size_t)n_pids * 8, '\0'), off_h((size_t)n_pids * 8, '\0');
+  int64_t* lens = reinterpret_cast<int64_t*>(&lens_h[0]);
+  int64_t* off = reinterpret_cast<int64_t*>(&off_h[0]);
+  CB_CUDA(cudaMemcpy(lens, d_lens, sizeof(int64_t) * n_pids, cudaMemcpyDeviceToHost));
+  int64_t total = 0;
+  const int64_t long_limit = 2 * TC_MAX_BROWS;
+  for (int64_t i = 0; i < n_pids; i++) {
+    CB_REQUIRE(lens[i] >= 0, CB_ERR_BOUNDS, "pid out of range 1:%lld (+ pid_base)", (long long)ix->Np);
+    CB_REQUIRE(lens[i] <= long_limit, CB_ERR_UNSUPPORTED, "passage longer than the tcgen05 kernel takes (%lld tokens)", (long long)lens[i]);
+    off[i] = total;
+    total += lens[i];
+  }
+  CB_REQUIRE(total <= capacity_rows, CB_ERR_BAD_ARG, "output buffers hold %lld rows, %lld needed", (long long)capacity_rows, (long long)total);
+  if (total == 0) return CB_OK;
+  CB_CUDA(cudaMemcpy(d_off, off, sizeof(int64_t) * n_pids, cudaMemcpyHostToDevice));
+  __half* d_out = nullptr;
+  CB_CUDA(cudaMalloc((void**)&d_out, (size_t)total * TC_DIM * 2 * 2));
+  G g2{d_out};
+  CB_CUDA(cudaMemset(d_out, 0, (size_t)total * TC_DIM * 2 * 2));
+  TcParams P{};
+  P.centroids_h = ix->centroids_h; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;
+  P.offsets = ix->offsets; P.Np = ix->Np; P.R = ix->R; P.long_limit = (int)long_limit;
+  const size_t smem = 1024 + (size_t)(2 * TC_MAX_BROWS + 32) * 256 + TC_LUT_BYTES + 128;
+#define CB_TC_DUMP(NB)                                                                                          \
+  do {                                                                                                          \
+    CB_CUDA(cudaFuncSetAttribute(k_tc_dump<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    k_tc_dump<NB><<<(unsigned)n_pids, 32 * TC_TEAM_WARPS, smem>>>(P, d_local, d_off, d_out, d_out + total * TC_DIM); \
+  } while (0)
+  if (ix->nbits == 1) CB_TC_DUMP(1);
+  else if (ix->nbits == 2) CB_TC_DUMP(2);
+  else CB_TC_DUMP(4);
+#undef CB_TC_DUMP
+  CB_LAUNCH_CHECK();
+  CB_CUDA(cudaMemcpy(out_norm, d_out, (size_t)total * TC_DIM * 2, cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(out_raw, d_out + total * TC_DIM, (size_t)total * TC_DIM * 2, cudaMemcpyDeviceToHost));
   return CB_OK;
 }

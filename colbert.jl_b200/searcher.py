@@ -224,6 +224,16 @@ class Searcher:
         L.check(L.load().cb_score_pids(self._h, _ptr(Qc), Qc.shape[1], _ptr(pids), len(pids), _ptr(out)))
         return out
 
+    def debug_tc_operand(self, pids, n_rows: int):
+        """Parity hook: the fp16 operand rows the tcgen05 scoring kernel's decompression produces for
+        `pids` (1-based): (normalised (n_rows, dim) float16, un-normalised centroid+weight (n_rows, dim)
+        float16), passages concatenated in the order given.  n_rows = sum of their doclens."""
+        pids = _c(pids, np.int64)
+        norm = np.zeros((n_rows, self.config.dim), dtype=np.float16)
+        raw = np.zeros((n_rows, self.config.dim), dtype=np.float16)
+        L.check(L.load().cb_debug_tc_operand(self._h, _ptr(pids), len(pids), _ptr(norm), _ptr(raw), n_rows))
+        return norm, raw
+
 
 def search(searcher: Searcher, Q, k: int):
     """`search(searcher, query, k)` (src/searching.jl:93-128) minus `encode_queries`: Q is the

@@ -178,6 +178,18 @@ int32_t cb_maxsim(int32_t device, int32_t dim, int32_t T, const float* Q, const 
 int32_t cb_score_pids(cb_index* index, const float* Q, int32_t T, const int64_t* pids,
                       int64_t n_pids, float* out_scores);
 
+/* Parity hook for the FUSED path: what the decompression stage of the tcgen05 scoring kernel writes into its
+ * shared-memory operand tiles for the listed passages (1-based pids + pid_base), produced by the very device
+ * functions the hot kernel runs (`decompress`, src/indexing/codecs/residual.jl:759-784, with `_unpackbits` /
+ * `_unbinarize` / `bucket_weights[idx]` 698-721 and `_normalize_array!`, src/utils.jl:320-325, in packed fp16):
+ *   out_norm uint16 (IEEE fp16 bits) [sum of doclens][dim]  normalised operand rows, passage after passage
+ *   out_raw  uint16 (IEEE fp16 bits) [sum of doclens][dim]  fp16(centroid) + fp16(w[bucket]) before normalisation --
+ *            exactly reproducible on the host, so it pins every unpacked bucket index of that code path.
+ * capacity_rows = rows both buffers hold.  CB_ERR_UNSUPPORTED when the index shape (dim != 128, nbits not in
+ * {1,2,4}) or a listed passage (> 480 tokens) is not taken by that kernel. */
+int32_t cb_debug_tc_operand(cb_index* index, const int64_t* pids, int64_t n_pids, uint16_t* out_norm,
+                            uint16_t* out_raw, int64_t capacity_rows);
+
 /* Stage 5 across shards: merges `n_lists` per-shard result lists (host, each [nq][k], unfilled
  * slots pid 0 / -inf) into the global first-k by (score desc, pid asc) -- the order the
  * reference's stable `sortperm(scores, rev=true)` over ascending pids produces

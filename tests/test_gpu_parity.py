@@ -400,3 +400,45 @@ def test_properties_medium_index():
         for q in range(2):
             want = np.unique(e2p[np.isin(ix["codes"], np.unique(cells[q]))])
             assert np.array_equal(s.retrieve(Q[q].T), want)
+
+
+# --------------------------------------------------------------------------------------------
+# the decompression of the FUSED tcgen05 kernel itself (not the fp32 hook): bucket indices bit-exact
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbits", [1, 2, 4])
+def test_fused_kernel_decompression_bit_exact(nbits):
+    """`north_star`: decompressed codes bit-exact.  cb_debug_tc_operand runs the device functions of the
+    hot kernel's decompression role (byte LUT, packed-fp16 add, normalisation, swizzled tile stores).
+    (1) fp16(centroid) + fp16(w[bucket]) is exactly reproducible in numpy float16, so equality pins every
+    unpacked bucket index of that code path (`_unpackbits`/`_unbinarize`, residual.jl:233-240, 428-441);
+    (2) the normalised operand equals fp16(oracle `decompress`) within 1 fp16 ulp (+ the 2^-11 relative
+    error the packed-fp16 norm carries).  Residual bytes cover all 256 values at every byte position."""
+    dim, K, Np = 128, 64, 96
+    r = np.random.default_rng(300 + nbits)
+    doclens = r.integers(1, 40, Np).astype(np.int64)
+    doclens[:6] = [1, 15, 16, 17, 240, 333]           # chunk-boundary cases: padding, 2-chunk passages
+    Ne = int(doclens.sum())
+    R = dim // 8 * nbits
+    res = r.integers(0, 256, (Ne, R), dtype=np.uint8)
+    res[:256, :] = np.arange(256, dtype=np.uint8)[:, None]          # every byte value at every byte position
+    res[256:512, :] = (np.arange(256, dtype=np.uint8)[:, None] + np.arange(R, dtype=np.uint8)[None, :] * 37)
+    codes = r.integers(1, K + 1, Ne).astype(np.uint32)
+    cen = O._normalize_array(r.standard_normal((dim, K)).astype(np.float32))
+    w = S.bucket_weights(nbits)
+    ivf, ivf_lengths = O._build_ivf(codes.astype(np.int64), K)
+    ix = dict(dim=dim, nbits=nbits, centroids=cen.T.copy(), bucket_weights=w, ivf=ivf, ivf_lengths=ivf_lengths,
+              doclens=doclens, codes=codes, residuals=res)
+    with make_searcher(ix) as s:
+        norm, raw = s.debug_tc_operand(np.arange(1, Np + 1), Ne)
+    idx = O.unpack_bucket_indices(dim, nbits, res.T).T                 # (Ne, dim) bucket indices, oracle
+    c16 = cen.T.astype(np.float16)[codes.astype(np.int64) - 1]         # fp16(centroid row)
+    w16 = w.astype(np.float16)[idx]
+    expect_raw = (c16 + w16).astype(np.float16)                        # one correctly rounded fp16 add, like __hadd2
+    assert np.array_equal(raw.view(np.uint16), expect_raw.view(np.uint16))
+    # distinct weights -> the raw value identifies the bucket index for every (embedding, dim)
+    assert len(np.unique(w.astype(np.float16))) == len(w)
+    o_emb = O.decompress(dim, nbits, cen, w, codes, res.T).T           # fp32 oracle (Ne, dim)
+    o16 = o_emb.astype(np.float16)
+    ulp = np.spacing(np.abs(o16)).astype(np.float32)
+    err = np.abs(norm.astype(np.float32) - o_emb)
+    assert np.all(err <= 1.5 * ulp + 2.0 ** -10 * np.abs(o_emb) + 1e-7), float((err / (ulp + 1e-12)).max())
