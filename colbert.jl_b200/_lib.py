@@ -24,6 +24,8 @@ SIGNATURES = {
     "cb_get_stat": (C.c_int32, [_p, C.c_char_p, C.POINTER(C.c_double)]),
     "cb_search_batch": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     "cb_search_batch_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
+    "cb_probe_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
+    "cb_search_batch_cells_device": (C.c_int32, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "cb_search_batch_plaid": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _p, _p, _p]),
     "cb_search_batch_plaid_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "cb_probe": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),

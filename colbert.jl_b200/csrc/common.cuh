@@ -19,7 +19,8 @@ constexpr int CB_NQ_CHUNK = 1024;      // queries scored per pass (bitmap row = 
 constexpr int CB_TOPR = 16;            // approximate per-token shortlist kept by stage 1
 constexpr int CB_MAX_NPROBE = 12;      // nprobe + margin must fit CB_TOPR
 constexpr int CB_MAX_K = 1024;         // top-k selection sorts its k winners in shared memory
-constexpr int CB_S1_SPLITS = 8;        // centroid-range splits of the SIMT stage-1 kernel
+constexpr int CB_S1_SPLITS = 16;       // most centroid-range segments one query token's shortlists can come in (tcgen05 stage 1)
+constexpr int CB_S1_SIMT_SPLITS = 8;   // centroid-range splits of the SIMT stage-1 kernel
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (never throw across the ABI)
@@ -104,6 +105,7 @@ struct cb_index {
   __half* centroids_h = nullptr;     // [K][dim] fp16 (fused fast path gather)
   uint8_t* centroids_img = nullptr;  // fp16 row image (swizzled MMA operand tiles) for the tcgen05 stage 1; dim = 128 only
   float centroid_norm_max = 1.f;     // max |centroid| (scales the fp16 rounding guard of stage 1)
+  float weight_abs_max = 0.f;        // max |bucket weight| (with the above: range precondition of the packed-fp16 decompression)
   float* weights = nullptr;          // [2^nbits]
   int32_t* codes = nullptr;          // [Ne] 0-based
   uint8_t* residuals = nullptr;      // [Ne][R]
@@ -112,13 +114,22 @@ struct cb_index {
   int32_t* ivf_pids = nullptr;       // [Ne]   local 0-based pid of every IVF entry
   size_t resident_bytes = 0;
   int64_t max_doclen = 0;
+  int64_t max_cell_len = 0;          // longest IVF cell: bounds the pair list of a batch without a host round trip
   int32_t n_long = -1, long_limit = 0;  // passages too long for the tcgen05 tile (cached list)
 
   // workspace (grow-only)
   DevBuf q_f32, q_prep, topr_val, topr_idx, cells, cell_scores, flags, bitmap, counts, list_off,
       cursors, pairs, out_pids, out_scores, out_counts, misc, long_list, hook_a, hook_b, hook_c, s1_thr, s1_thr0,
-      bitmap_t, bitmap2, pl_ents, pl_misc, pl_vec, pl_next, pl_head, pl_mask, pl_active, pl_top_pids, pl_top_scores, pl_sel, pl_npos;   // PLAID mode (plaid.cu)
-  int64_t* pinned_total = nullptr;  // pinned host scalar(s) for the one D2H per batch
+      bitmap_t, bitmap2, q_flag, fin_keys, fin_pids, fin_scores, pl_ents, pl_misc, pl_vec, pl_next, pl_head, pl_mask, pl_active, pl_top_pids, pl_top_scores, pl_sel, pl_npos;   // PLAID mode (plaid.cu)
+  int64_t* pinned_total = nullptr;  // pinned host scalars (synchronous paths: hooks, PLAID mode)
+  // Batch counters live on the device ([0] pairs, [1] pair embeddings, [2] stage-1 rows re-done by the exact
+  // scan, [3] query batches outside the tcgen05 kernel's range); they are copied to pinned memory at the end
+  // of a batch and read lazily by cb_get_stat, so the search itself never waits for the host.
+  DevBuf d_stats;
+  unsigned long long* pinned_stats = nullptr;
+  cudaEvent_t ev_stats = nullptr;
+  bool stats_pending = false;
+  int stats_tc_selected = 0;
   const float* q_prep_src = nullptr; // q_prep currently holds the row image of these query tokens ...
   int64_t q_prep_rows = 0;           // ... (this many rows); reset at the start of every search chunk
   // what the last cb_stage1_probe left in topr_val / topr_idx / s1_thr0 (read by the PLAID survivor pass)
@@ -132,10 +143,12 @@ struct cb_index {
   int opt_stage1_impl = 0;
   int opt_profile = 0;
   int opt_tc_astages = 0;   // query-tile stages of the tcgen05 scoring kernel (0 = default)
+  int opt_sync_pairs = 0;   // 1 = size the pair list with a host round trip (exact) instead of the IVF bound
+  int opt_exact_rescore = 1;   // final top-k decided on exact fp32 scores of the best 2k+ tensor-core candidates
 
   // stats of the last search
   long long st_launches = 0;
-  double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0, st_s1_tc_rows = 0;
+  double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0, st_s1_tc_rows = 0, st_rescore_unsafe = 0, st_bad_cells = 0;
   double st_ms[5] = {0, 0, 0, 0, 0};  // stage1, stage2, stage34, stage5, total
   double st_plaid_survivors = 0, st_plaid_positive = 0, st_plaid_rescored = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -144,6 +157,8 @@ struct cb_index {
 // ---------------------------------------------------------------------------------------------
 // stage launchers (defined in the stage*.cu files)
 // ---------------------------------------------------------------------------------------------
+inline unsigned long long* cb_stats_dev(cb_index* ix) { return ix->d_stats.as<unsigned long long>(); }
+
 // Stage 1: per query-token row, the top-`nprobe` centroids of Q . C^T (exact fp32 decision).
 // d_cells int32[nrows][nprobe] 0-based; d_scores float[nrows][nprobe]; flagged count to stats.
 int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe, int32_t* d_cells,
@@ -155,28 +170,33 @@ int32_t cb_stage2_mark(cb_index* ix, const int32_t* d_cells, int nq, int T, int 
 
 // Stages 1+2 for one chunk of <= CB_NQ_CHUNK queries (search.cu): leaves bitmap / counts / list_off / zeroed
 // cursors in the workspace and returns the number of (query, passage) pairs of the chunk.
+// total_pairs == nullptr: no host round trip (the caller sizes the pair list from cb_pair_bound).
+// d_cells_in != nullptr: stage 1 is skipped, the chunk's cells ([nq][T][nprobe], 0-based, -1 = none) are given.
 int32_t cb_candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int nprobe, int W, cudaStream_t st,
-                            int64_t* total_pairs);
+                            int64_t* total_pairs, const int32_t* d_cells_in = nullptr);
 
 // Exclusive scan of counts -> list offsets (+ total in list_off[nq]).
-int32_t cb_scan_counts(const int32_t* d_counts, int nq, int64_t* d_list_off, cudaStream_t st);
+int32_t cb_scan_counts(const int32_t* d_counts, int nq, int64_t* d_list_off, cudaStream_t st,
+                       unsigned long long* d_stat_pairs = nullptr);
 
 // Stages 3+4: for every (passage, candidate query) pair appends a 64-bit key
 // (orderable score << 32 | ~local_pid) to the query's list.
 int32_t cb_stage34_score(cb_index* ix, const float* dQ, int nq, int T, int W,
                          const uint32_t* d_bitmap, const int64_t* d_list_off, int32_t* d_cursors,
                          uint64_t* d_pairs, cudaStream_t st);
+// d_gate != nullptr: the kernel does nothing unless *d_gate != 0 (device-side routing, no host round trip).
 int32_t cb_stage34_generic(cb_index* ix, const float* dQ, int nq, int T, int W,
                            const uint32_t* d_bitmap, const int32_t* d_pid_list, int64_t n_list,
                            const int64_t* d_list_off, int32_t* d_cursors, uint64_t* d_pairs,
-                           cudaStream_t st);
+                           cudaStream_t st, const int* d_gate = nullptr);
 int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W,
                       const uint32_t* d_bitmap, const int64_t* d_list_off, int32_t* d_cursors,
                       uint64_t* d_pairs, cudaStream_t st);
 bool cb_stage34_tc_supported(const cb_index* ix, int T);
 // fp32 rows [nrows][128] -> fp16 "row image" [nrows_pad/8][2 K-blocks][8 rows][128 B] (SWIZZLE_128B
 // K-major, 2048 B between 8-row groups): the shared-memory operand layout of both tcgen05 kernels.
-int32_t cb_tc_prep_rows(const float* dX, int64_t nrows, int64_t nrows_pad, uint8_t* d_out, cudaStream_t st);
+// d_range_flag (optional): set to 1 when a row breaks the |row| <= 255 precondition of the tcgen05 scoring kernel.
+int32_t cb_tc_prep_rows(const float* dX, int64_t nrows, int64_t nrows_pad, uint8_t* d_out, cudaStream_t st, int* d_range_flag = nullptr);
 
 // Stage 5: first k of each query's list by key descending -> 1-based global pids / scores.
 int32_t cb_stage5_topk(const uint64_t* d_pairs, const int64_t* d_list_off, int nq, int k,

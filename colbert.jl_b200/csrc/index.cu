@@ -128,6 +128,17 @@ __global__ void k_cell_offsets_from_sorted(const uint32_t* __restrict__ keys, in
   cell_offsets[c] = lo;
 }
 
+__global__ void k_max_cell_len(const int64_t* __restrict__ cell_offsets, int64_t K, unsigned long long* __restrict__ out) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long m = 0;
+  for (; c < K; c += stride) {
+    const unsigned long long len = (unsigned long long)(cell_offsets[c + 1] - cell_offsets[c]);
+    if (len > m) m = len;
+  }
+  if (m) atomicMax(out, m);
+}
+
 static inline int grid_for(int64_t n, int threads = 256) {
   int64_t b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -163,10 +174,12 @@ static void destroy_index(cb_index* ix) {
   DevBuf* bufs[] = {&ix->q_f32, &ix->q_prep, &ix->topr_val, &ix->topr_idx, &ix->cells, &ix->cell_scores,
                     &ix->flags, &ix->bitmap, &ix->counts, &ix->list_off, &ix->cursors, &ix->pairs,
                     &ix->out_pids, &ix->out_scores, &ix->out_counts, &ix->misc, &ix->long_list,
-                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0, &ix->bitmap_t, &ix->bitmap2, &ix->pl_ents, &ix->pl_misc,
+                    &ix->hook_a, &ix->hook_b, &ix->hook_c, &ix->s1_thr, &ix->s1_thr0, &ix->bitmap_t, &ix->bitmap2, &ix->q_flag, &ix->d_stats, &ix->fin_keys, &ix->fin_pids, &ix->fin_scores, &ix->pl_ents, &ix->pl_misc,
                     &ix->pl_vec, &ix->pl_next, &ix->pl_head, &ix->pl_mask, &ix->pl_active, &ix->pl_top_pids, &ix->pl_top_scores, &ix->pl_sel, &ix->pl_npos};
   for (DevBuf* b : bufs) b->release();
   if (ix->pinned_total) cudaFreeHost(ix->pinned_total);
+  if (ix->pinned_stats) cudaFreeHost(ix->pinned_stats);
+  if (ix->ev_stats) cudaEventDestroy(ix->ev_stats);
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
   cudaGetLastError();
   delete ix;
@@ -198,6 +211,14 @@ static int32_t create_impl(cb_index* ix, const float* centroids, const float* bu
   CB_DEVALLOC(ix->weights, sizeof(float) * (1u << ix->nbits));
   CB_TRY(upload(ix->centroids, centroids, sizeof(float) * K * dim, flags));
   CB_TRY(upload(ix->weights, bucket_weights, sizeof(float) * (1u << ix->nbits), flags));
+  {
+    float hw[1 << CB_MAX_NBITS];
+    CB_CUDA(cudaMemcpy(hw, ix->weights, sizeof(float) * (1u << ix->nbits), cudaMemcpyDeviceToHost));
+    for (unsigned i = 0; i < (1u << ix->nbits); i++) {
+      const float a = hw[i] < 0 ? -hw[i] : hw[i];
+      if (!(a <= ix->weight_abs_max)) ix->weight_abs_max = a;   // (a NaN weight sticks: the tcgen05 path is then refused)
+    }
+  }
   k_f32_to_f16<<<grid_for(K * dim), 256>>>(ix->centroids, ix->centroids_h, K * dim);
   CB_LAUNCH_CHECK();
   {  // largest centroid norm; (dim = 128) the swizzled fp16 operand image of the tcgen05 stage 1
@@ -305,6 +326,21 @@ static int32_t create_impl(cb_index* ix, const float* centroids, const float* bu
     CB_LAUNCH_CHECK();
     CB_CUDA(cudaDeviceSynchronize());
   }
+  {  // longest IVF cell (bounds a batch's pair list without a host round trip, search.cu)
+    CB_CUDA(cudaMemset(d_max, 0, sizeof(unsigned long long)));
+    k_max_cell_len<<<grid_for(K), 256>>>(ix->cell_offsets, K, d_max);
+    CB_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    CB_CUDA(cudaMemcpy(&h, d_max, sizeof(h), cudaMemcpyDeviceToHost));
+    ix->max_cell_len = (int64_t)h;
+  }
+  CB_TRY(ix->d_stats.ensure(64));
+  CB_CUDA(cudaMemset(ix->d_stats.p, 0, 64));
+  CB_TRY(ix->q_flag.ensure(sizeof(int)));
+  CB_CUDA(cudaMemset(ix->q_flag.p, 0, sizeof(int)));
+  CB_CUDA(cudaHostAlloc((void**)&ix->pinned_stats, 64, cudaHostAllocDefault));
+  memset(ix->pinned_stats, 0, 64);
+  CB_CUDA(cudaEventCreateWithFlags(&ix->ev_stats, cudaEventDisableTiming));
   CB_CUDA(cudaHostAlloc((void**)&ix->pinned_total, 64, cudaHostAllocDefault));
   for (auto& e : ix->ev) CB_CUDA(cudaEventCreate(&e));
   CB_CUDA(cudaDeviceSynchronize());
@@ -366,12 +402,25 @@ extern "C" int32_t cb_set_option(cb_index* ix, const char* key, int64_t value) {
   else if (!strcmp(key, "stage1_impl")) ix->opt_stage1_impl = (int)value;
   else if (!strcmp(key, "profile")) ix->opt_profile = (int)value;
   else if (!strcmp(key, "tc_astages")) ix->opt_tc_astages = (int)value;
+  else if (!strcmp(key, "sync_pairs")) ix->opt_sync_pairs = (int)value;
+  else if (!strcmp(key, "exact_rescore")) ix->opt_exact_rescore = (int)value;
   else { cb_set_error("unknown option '%s'", key); return CB_ERR_BAD_ARG; }
   return CB_OK;
 }
 
-extern "C" int32_t cb_get_stat(const cb_index* ix, const char* key, double* value) {
-  CB_REQUIRE(ix && key && value, CB_ERR_BAD_ARG, "NULL argument");
+extern "C" int32_t cb_get_stat(const cb_index* cix, const char* key, double* value) {
+  CB_REQUIRE(cix && key && value, CB_ERR_BAD_ARG, "NULL argument");
+  cb_index* ix = const_cast<cb_index*>(cix);
+  if (ix->stats_pending) {   // the batch counters were copied to pinned memory at the end of the batch: wait for that copy only now
+    CB_CUDA(cudaSetDevice(ix->device));
+    CB_CUDA(cudaEventSynchronize(ix->ev_stats));
+    ix->stats_pending = false;
+    const unsigned long long* h = ix->pinned_stats;
+    ix->st_pairs = (double)h[0]; ix->st_pair_embs = (double)h[1]; ix->st_flagged = (double)h[2];
+    ix->st_tc_pairs = (ix->stats_tc_selected && h[3] == 0) ? (double)h[0] : 0.0;
+    ix->st_generic_pairs = (double)h[0] - ix->st_tc_pairs;
+    ix->st_bad_cells = (double)h[4]; ix->st_rescore_unsafe = (double)h[5];
+  }
   if (!strcmp(key, "launches")) *value = (double)ix->st_launches;
   else if (!strcmp(key, "pairs")) *value = ix->st_pairs;
   else if (!strcmp(key, "pair_embeddings")) *value = ix->st_pair_embs;
@@ -381,6 +430,9 @@ extern "C" int32_t cb_get_stat(const cb_index* ix, const char* key, double* valu
   else if (!strcmp(key, "plaid_candidates")) *value = ix->st_plaid_positive;
   else if (!strcmp(key, "plaid_rescored")) *value = ix->st_plaid_rescored;
   else if (!strcmp(key, "generic_pairs")) *value = ix->st_generic_pairs;
+  else if (!strcmp(key, "rescore_unsafe")) *value = ix->st_rescore_unsafe;
+  else if (!strcmp(key, "bad_cells")) *value = ix->st_bad_cells;
+  else if (!strcmp(key, "max_cell_len")) *value = (double)ix->max_cell_len;
   else if (!strcmp(key, "stage1_tc_rows")) *value = ix->st_s1_tc_rows;
   else if (!strcmp(key, "ms_stage1")) *value = ix->st_ms[0];
   else if (!strcmp(key, "ms_stage2")) *value = ix->st_ms[1];

@@ -57,7 +57,7 @@ k_plaid_emit(const float* __restrict__ Q, int64_t nrows, int T, const float* __r
   const unsigned long long qid = (unsigned long long)(row / T);
   for (int ci = lane; ci < ncand; ci += 32) {
     const int32_t cid = topi[row * ncand + ci];
-    if (cid == 0x7fffffff) continue;
+    if ((uint32_t)cid >= 0x7fffffffu) continue;   // empty slot (0x7fffffff) or a segment that does not exist (-1)
     if ((ci % CB_TOPR) == CB_TOPR - 1) excluded = fmaxf(excluded, topv[row * ncand + ci]);
     const float sc = pl_fixed_dot(q, C + (int64_t)cid * dim, dim);
     if (sc >= thr) {
@@ -258,8 +258,8 @@ k_plaid_fill(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ bitmap2
 
 }  // namespace
 
-int32_t cb_candidates_chunk(cb_index* ix, const float* dQ, int nq, int T, int nprobe, int W, cudaStream_t st,
-                            int64_t* total_pairs);   // search.cu
+int32_t cb_final_topk(cb_index* ix, const float* dQ, int nq, int T, int k, const uint64_t* d_pairs, const int64_t* d_list_off,
+                      const int32_t* d_lens, int64_t* d_out_pids, float* d_out_scores, cudaStream_t st);   // stage5.cu
 
 extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, int32_t nq, int32_t T, int32_t ncells,
                                                 float centroid_score_threshold, int32_t ndocs, int32_t k,
@@ -277,6 +277,7 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
   const long long launches0 = g_cb_launches;
   ix->st_pairs = ix->st_pair_embs = ix->st_flagged = ix->st_tc_pairs = ix->st_generic_pairs = ix->st_s1_tc_rows = 0;
   ix->st_plaid_survivors = ix->st_plaid_positive = ix->st_plaid_rescored = 0;
+  CB_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 64, st));
   for (int q0 = 0; q0 < nq; q0 += CB_NQ_CHUNK) {
     const int n = (nq - q0 < CB_NQ_CHUNK) ? nq - q0 : CB_NQ_CHUNK;
     const int W = (n + 31) / 32;
@@ -394,10 +395,11 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
       ix->tc_active_n = 0;
       CB_TRY(rc);
     }
-    CB_TRY(cb_stage5_topk(ix->pairs.as<uint64_t>(), ix->list_off.as<int64_t>(), n, k, ix->pid_base,
-                          d_out_pids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, st));
+    CB_TRY(cb_final_topk(ix, dQc, n, T, k, ix->pairs.as<uint64_t>(), ix->list_off.as<int64_t>(), nullptr,
+                         d_out_pids + (int64_t)q0 * k, d_out_scores + (int64_t)q0 * k, st));
     CB_CUDA(cudaMemcpyAsync(d_out_counts + q0, ix->pl_sel.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st));
   }
+  ix->stats_pending = false;   // this mode keeps its counters on the host (it synchronises per chunk anyway)
   ix->st_launches = g_cb_launches - launches0;
   return CB_OK;
 }

@@ -127,16 +127,18 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
   if (row >= nrows) return;
   const float* q = Q + row * dim;
   const int ncand = nsplit * CB_TOPR;
-  float sc[4];
-  int32_t id[4];
+  constexpr int PER_LANE = CB_S1_SPLITS * CB_TOPR / 32;   // candidates per lane
+  float sc[PER_LANE];
+  int32_t id[PER_LANE];
   float excluded = -INFINITY;  // best approximate score any NON-shortlisted centroid can have
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
+  for (int j = 0; j < PER_LANE; j++) {
     int ci = lane + 32 * j;
     sc[j] = -INFINITY;
     id[j] = 0x7fffffff;
     if (ci < ncand) {
       int32_t cid = topi[row * ncand + ci];
+      if (cid < 0) cid = 0x7fffffff;   // a segment that does not exist for this row (stage1_tc.cu)
       if (cid != 0x7fffffff) {
         sc[j] = fixed_order_dot(q, C + (int64_t)cid * dim, dim);
         id[j] = cid;
@@ -160,7 +162,7 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
     // lane-local best
     float bs = -INFINITY; int32_t bi = 0x7fffffff; int bj = -1;
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < PER_LANE; j++)
       if (id[j] != 0x7fffffff && (bj < 0 || s1_better(sc[j], id[j], bs, bi))) { bs = sc[j]; bi = id[j]; bj = j; }
     // warp argbest
     float ws = bs; int32_t wi = bi;
@@ -176,7 +178,7 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
     }
     if (bj >= 0 && bi == wi) {  // owner retires it (ids are unique per row)
 #pragma unroll
-      for (int j = 0; j < 4; j++) if (j == bj) id[j] = 0x7fffffff;
+      for (int j = 0; j < PER_LANE; j++) if (j == bj) id[j] = 0x7fffffff;
     }
     if (lane == 0) { cells[row * nprobe + p] = wi; cell_scores[row * nprobe + p] = ws; }
     last = ws;
@@ -187,14 +189,21 @@ k_stage1_rescore(const float* __restrict__ Q, int64_t nrows, const float* __rest
 // ---------------------------------------------------------------------------------------------
 // 3. exact scan of all K centroids for flagged rows (rare).  One CTA per flagged row.
 // ---------------------------------------------------------------------------------------------
+// The number of flagged rows stays on the device (flagged[0]): the grid is fixed and CTA b takes the rows
+// b, b + gridDim.x, ... of the list, so no host round trip sits between the shortlist pass and the scan.
 __global__ void __launch_bounds__(256)
 k_stage1_fullscan(const float* __restrict__ Q, const float* __restrict__ C, int64_t K, int dim, int nprobe,
-                  const int32_t* __restrict__ flagged_rows, int32_t* __restrict__ cells, float* __restrict__ cell_scores) {
+                  const int32_t* __restrict__ flagged /* [0] = count, [1..] = rows */, int32_t* __restrict__ cells,
+                  float* __restrict__ cell_scores, unsigned long long* __restrict__ stat_flagged) {
   extern __shared__ float s_q[];  // dim floats, then reduction scratch
   __shared__ float r_s[256];
   __shared__ int32_t r_i[256];
-  const int64_t row = flagged_rows[blockIdx.x];
   const int tid = threadIdx.x;
+  const int nflag = flagged[0];
+  if (blockIdx.x == 0 && tid == 0 && stat_flagged != nullptr && nflag > 0) atomicAdd(stat_flagged, (unsigned long long)nflag);
+  for (int fi = blockIdx.x; fi < nflag; fi += gridDim.x) {
+  const int64_t row = flagged[1 + fi];
+  __syncthreads();
   for (int k = tid; k < dim; k += 256) s_q[k] = Q[row * dim + k];
   __syncthreads();
   float ls[CB_MAX_NPROBE];
@@ -231,6 +240,7 @@ k_stage1_fullscan(const float* __restrict__ Q, const float* __restrict__ C, int6
       cell_scores[row * nprobe + p] = (wi == 0x7fffffff) ? -INFINITY : ws;
     }
   }
+  }
 }
 
 // compacts flagged row ids; count in out[0], ids in out[1..]
@@ -250,7 +260,7 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
   CB_REQUIRE(nprobe >= 1 && nprobe <= CB_MAX_NPROBE, CB_ERR_UNSUPPORTED, "nprobe must be in 1..%d (got %d)",
              CB_MAX_NPROBE, nprobe);
   if (nrows == 0) return CB_OK;
-  int nsplit = CB_S1_SPLITS;
+  int nsplit = CB_S1_SIMT_SPLITS;
   if (ix->K < 4096) nsplit = 1;
   CB_TRY(ix->topr_val.ensure(sizeof(float) * nrows * CB_S1_SPLITS * CB_TOPR));
   CB_TRY(ix->topr_idx.ensure(sizeof(int32_t) * nrows * CB_S1_SPLITS * CB_TOPR));
@@ -259,7 +269,8 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
   int32_t* topi = ix->topr_idx.as<int32_t>();
   int32_t* flags = ix->flags.as<int32_t>();
   int32_t* flagged = flags + nrows;  // [0] = count, [1..] = row ids
-  float guard = 1e-5f, guard_rel = 0.f;
+  // the SIMT pass's fmaf chain and the fixed-order dot differ by <= ~2 dim 2^-24 |q||c|: scale with |q|, max|c|
+  float guard = 1e-5f, guard_rel = 2.0f * (float)ix->dim * 5.9604645e-08f * ix->centroid_norm_max;
 
   bool used_tc = false;
   CB_TRY(ix->s1_thr0.ensure(sizeof(float) * nrows * CB_S1_SPLITS));
@@ -282,15 +293,10 @@ int32_t cb_stage1_probe(cb_index* ix, const float* dQ, int64_t nrows, int nprobe
   CB_CUDA(cudaMemsetAsync(flagged, 0, sizeof(int32_t), st));
   k_compact_flags<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(flags, nrows, flagged);
   CB_LAUNCH_CHECK();
-  int32_t nflag = 0;
-  CB_CUDA(cudaMemcpyAsync(ix->pinned_total + 4, flagged, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
-  nflag = *reinterpret_cast<int32_t*>(ix->pinned_total + 4);
-  ix->st_flagged += nflag;
-  if (nflag > 0) {
-    k_stage1_fullscan<<<nflag, 256, sizeof(float) * ix->dim, st>>>(dQ, ix->centroids, ix->K, ix->dim, nprobe,
-                                                                    flagged + 1, d_cells, d_scores);
-    CB_LAUNCH_CHECK();
-  }
+  // flagged rows are rare (a handful per batch on well-separated queries): a fixed, modest grid covers them
+  const int64_t fs_grid = nrows < 2 * ix->sm_count ? nrows : 2 * ix->sm_count;
+  k_stage1_fullscan<<<(unsigned)fs_grid, 256, sizeof(float) * ix->dim, st>>>(dQ, ix->centroids, ix->K, ix->dim, nprobe, flagged,
+                                                                            d_cells, d_scores, cb_stats_dev(ix) + 2);
+  CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -100,9 +100,7 @@ k_bitmap_transpose(const uint32_t* __restrict__ bitmapT, int nq, int64_t NpW, in
 int32_t cb_stage2_mark(cb_index* ix, const int32_t* d_cells, int nq, int T, int nprobe, int W,
                        uint32_t* d_bitmap, int32_t* d_counts, cudaStream_t st) {
   if (nq == 0 || ix->Np == 0) return CB_OK;
-  CB_TRY(ix->misc.ensure(64));
-  unsigned long long* d_embs = ix->misc.as<unsigned long long>();
-  CB_CUDA(cudaMemsetAsync(d_embs, 0, sizeof(unsigned long long), st));
+  unsigned long long* d_embs = cb_stats_dev(ix) + 1;   // batch counter: pair embeddings
   const int64_t NpW = ((ix->Np + 31) / 32 + 7) / 8 * 8;   // words per query row, padded to whole 32-byte sectors
   CB_TRY(ix->bitmap_t.ensure(sizeof(uint32_t) * (size_t)nq * (size_t)NpW));
   CB_CUDA(cudaMemsetAsync(ix->bitmap_t.p, 0, sizeof(uint32_t) * (size_t)nq * (size_t)NpW, st));
@@ -117,7 +115,7 @@ int32_t cb_stage2_mark(cb_index* ix, const int32_t* d_cells, int nq, int T, int 
 
 // Exclusive scan of the per-query candidate counts (nq <= CB_NQ_CHUNK): one CTA.
 __global__ void __launch_bounds__(1024)
-k_scan_counts(const int32_t* __restrict__ counts, int nq, int64_t* __restrict__ list_off) {
+k_scan_counts(const int32_t* __restrict__ counts, int nq, int64_t* __restrict__ list_off, unsigned long long* __restrict__ stat_pairs) {
   __shared__ int64_t s[1024];
   int tid = threadIdx.x;
   int64_t v = tid < nq ? counts[tid] : 0;
@@ -130,12 +128,15 @@ k_scan_counts(const int32_t* __restrict__ counts, int nq, int64_t* __restrict__ 
     __syncthreads();
   }
   if (tid < nq) list_off[tid] = s[tid] - v;
-  if (tid == 1023) list_off[nq] = s[1023];
+  if (tid == 1023) {
+    list_off[nq] = s[1023];
+    if (stat_pairs != nullptr) atomicAdd(stat_pairs, (unsigned long long)s[1023]);
+  }
 }
 
-int32_t cb_scan_counts(const int32_t* d_counts, int nq, int64_t* d_list_off, cudaStream_t st) {
+int32_t cb_scan_counts(const int32_t* d_counts, int nq, int64_t* d_list_off, cudaStream_t st, unsigned long long* d_stat_pairs) {
   CB_REQUIRE(nq <= 1024, CB_ERR_BAD_ARG, "internal: scan chunk too large");
-  k_scan_counts<<<1, 1024, 0, st>>>(d_counts, nq, d_list_off);
+  k_scan_counts<<<1, 1024, 0, st>>>(d_counts, nq, d_list_off, d_stat_pairs);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

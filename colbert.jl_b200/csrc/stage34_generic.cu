@@ -26,6 +26,7 @@ struct GenericParams {
   unsigned long long* work;       // dynamic work counter
   const int64_t* list_off; int32_t* cursors; uint64_t* pairs;  // pair-list output (bitmap mode)
   float* out_scores;              // [n_items][nq] direct output (hook mode) or nullptr
+  const int* gate;                // optional: run only when *gate != 0
 };
 
 __global__ void __launch_bounds__(G_THREADS)
@@ -41,6 +42,7 @@ k_maxsim_generic(GenericParams P) {
   __shared__ int s_ncand;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = G_THREADS / 32;
+  if (P.gate != nullptr && *P.gate == 0) return;
   for (int i = tid; i < (1 << P.nbits); i += G_THREADS) s_w[i] = P.weights[i];
   const float eps = 1.1920929e-07f;  // eps(Float32)
 
@@ -170,8 +172,9 @@ static void fill_index_params(const cb_index* ix, GenericParams& P) {
 
 int32_t cb_stage34_generic(cb_index* ix, const float* dQ, int nq, int T, int W, const uint32_t* d_bitmap,
                            const int32_t* d_pid_list, int64_t n_list, const int64_t* d_list_off,
-                           int32_t* d_cursors, uint64_t* d_pairs, cudaStream_t st) {
+                           int32_t* d_cursors, uint64_t* d_pairs, cudaStream_t st, const int* d_gate) {
   GenericParams P{};
+  P.gate = d_gate;
   fill_index_params(ix, P);
   P.T = T; P.nq = nq; P.W = W; P.Q = dQ; P.bitmap = d_bitmap; P.pid_list = d_pid_list;
   P.n_items = d_pid_list ? n_list : ix->Np;
@@ -187,4 +190,85 @@ int32_t cb_generic_score_list(cb_index* ix, const float* dQ, int nq, int T, cons
   P.T = T; P.nq = nq; P.W = 0; P.Q = dQ; P.bitmap = nullptr; P.pid_list = d_pid_list; P.n_items = n_list;
   P.out_scores = d_out_scores;
   return launch_generic(ix, P, ix->max_doclen, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact fp32 re-score of explicit (query, passage) pairs: the decision pass behind the final top-k.
+// pids int64[nq][K2] (1-based global, 0 = empty slot); scores_out float[nq][K2].  One CTA per pair; the
+// arithmetic is that of k_maxsim_generic above, operation for operation (decompress: c + w[b] rounded,
+// fmaf sum of squares, sqrt + eps, division; dot: fmaf chain over k ascending; fixed-order sum over query
+// tokens), so a score equals what cb_score_pids returns for the same pair bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int R_THREADS = 128, R_TOK = 16;
+
+__global__ void __launch_bounds__(R_THREADS)
+k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64_t pid_base, int64_t Np, float* __restrict__ scores_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int dim = P.dim, T = P.T, ld = dim + 1;
+  float* Qs = reinterpret_cast<float*>(smem_raw);                 // [T][ld]
+  float* Ds = Qs + (size_t)T * ld;                                // [R_TOK][ld]
+  uint32_t* tokmax = reinterpret_cast<uint32_t*>(Ds + (size_t)R_TOK * ld);   // [T]
+  float* s_w = reinterpret_cast<float*>(tokmax + T);              // [256]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = R_THREADS / 32;
+  const int q = blockIdx.x / K2;
+  const int64_t pid = pids[blockIdx.x];
+  if (pid <= 0) { if (tid == 0) scores_out[blockIdx.x] = -INFINITY; return; }
+  const int64_t p = pid - 1 - pid_base;
+  if (p < 0 || p >= Np) { if (tid == 0) scores_out[blockIdx.x] = -INFINITY; return; }
+  const int64_t e0 = P.offsets[p];
+  const int L = (int)(P.offsets[p + 1] - e0);
+  for (int i = tid; i < (1 << P.nbits); i += R_THREADS) s_w[i] = P.weights[i];
+  const float* __restrict__ qg = P.Q + (int64_t)q * T * dim;
+  for (int i = tid; i < T * dim; i += R_THREADS) Qs[(i / dim) * ld + (i % dim)] = qg[i];
+  for (int i = tid; i < T; i += R_THREADS) tokmax[i] = 0u;
+  const float eps = 1.1920929e-07f;
+  for (int c0 = 0; c0 < L; c0 += R_TOK) {
+    const int n = min(R_TOK, L - c0);
+    __syncthreads();
+    for (int e = warp; e < n; e += nwarps) {
+      const int64_t g = e0 + c0 + e;
+      const float* __restrict__ cptr = P.centroids + (int64_t)P.codes[g] * dim;
+      const uint8_t* __restrict__ emb = P.residuals + g * P.R;
+      float ss = 0.f;
+      for (int d = lane; d < dim; d += 32) {
+        float v = __fadd_rn(cptr[d], s_w[cb_bucket_of(emb, d, P.nbits)]);
+        Ds[e * ld + d] = v;
+        ss = fmaf(v, v, ss);
+      }
+      ss = cb_warp_sum(ss);
+      const float denom = __fadd_rn(sqrtf(ss), eps);
+      for (int d = lane; d < dim; d += 32) Ds[e * ld + d] = __fdiv_rn(Ds[e * ld + d], denom);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < T * n; idx += R_THREADS) {
+      const int t = idx % T, e = idx / T;
+      const float* a = Qs + t * ld;
+      const float* b = Ds + e * ld;
+      float acc = 0.f;
+      for (int k = 0; k < dim; k++) acc = fmaf(a[k], b[k], acc);
+      atomicMax(&tokmax[t], cb_orderable(acc));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    if (L == 0) s = -INFINITY;
+    else for (int t = 0; t < T; t++) s = __fadd_rn(s, cb_unorderable(tokmax[t]));
+    scores_out[blockIdx.x] = s;
+  }
+}
+
+int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, int K2, float* d_scores_out,
+                                 cudaStream_t st) {
+  if (nq == 0 || K2 == 0) return CB_OK;
+  GenericParams P{};
+  fill_index_params(ix, P);
+  P.T = T; P.nq = nq; P.Q = dQ;
+  const int ld = ix->dim + 1;
+  const size_t smem = ((size_t)(T + R_TOK) * ld + T + 256) * 4;
+  CB_REQUIRE(smem <= 200 * 1024, CB_ERR_UNSUPPORTED, "dim = %d, query length = %d do not fit the re-score kernel's shared memory", ix->dim, T);
+  CB_CUDA(cudaFuncSetAttribute(k_rescore_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_rescore_pairs<<<(unsigned)((int64_t)nq * K2), R_THREADS, smem, st>>>(P, d_pids, K2, ix->pid_base, ix->Np, d_scores_out);
+  CB_LAUNCH_CHECK();
+  return CB_OK;
 }

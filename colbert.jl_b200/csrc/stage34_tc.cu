@@ -82,6 +82,7 @@ struct TcParams {
   const uint8_t* qprep;           // query row image: [nq][8 KB]
   const uint32_t* bitmap; const int64_t* list_off; int32_t* cursors; uint64_t* pairs;
   const int32_t* pid_list; int64_t n_list;   // optional: only these passages (sparse bitmaps, e.g. the PLAID rescoring pass)
+  const int* q_flag;              // != 0: the batch breaks the |query token| <= 255 precondition; the generic kernel scores it
 };
 
 // max over 32 / 16 TMEM columns held in registers, folded into 4 independent chains
@@ -290,6 +291,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 template <int NBITS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_maxsim_tc(TcParams P) {
+  if (*P.q_flag != 0) return;   // whole grid, before any barrier / TMEM allocation
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align the dynamic window by hand
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -715,8 +717,12 @@ size_t tc_fixed_smem_bytes(int nbits) {
 
 }  // namespace
 
+// Shape: dim 128, 32 query tokens, nbits 1 / 2 / 4.  Range: the decompression squares centroid + weight in packed
+// fp16 (two-term chains), which overflows beyond ~180 per component: an index whose centroids or weights are not
+// of order 1 (every ColBERT index is: centroids are k-means means of unit vectors) goes to the generic fp32 kernel.
 bool cb_stage34_tc_supported(const cb_index* ix, int T) {
-  return ix->dim == TC_DIM && T == TC_T && (ix->nbits == 1 || ix->nbits == 2 || ix->nbits == 4);
+  return ix->dim == TC_DIM && T == TC_T && (ix->nbits == 1 || ix->nbits == 2 || ix->nbits == 4) &&
+         (ix->centroid_norm_max + ix->weight_abs_max <= 100.f);
 }
 
 __global__ void k_collect_long_tc(const int64_t* __restrict__ offsets, int64_t Np, int64_t limit,
@@ -750,7 +756,10 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   // per-batch query row image (fp16, swizzled): stage 1 has usually built it already
   if (ix->q_prep_src != dQ || ix->q_prep_rows != (int64_t)nq * TC_T) {
     CB_TRY(ix->q_prep.ensure((size_t)nq * TC_Q_BYTES));
-    CB_TRY(cb_tc_prep_rows(dQ, (int64_t)nq * TC_T, (int64_t)nq * TC_T, ix->q_prep.as<uint8_t>(), st));
+    CB_CUDA(cudaMemsetAsync(ix->q_flag.p, 0, sizeof(int), st));
+    CB_TRY(cb_tc_prep_rows(dQ, (int64_t)nq * TC_T, (int64_t)nq * TC_T, ix->q_prep.as<uint8_t>(), st, ix->q_flag.as<int>()));
+    ix->q_prep_src = dQ;
+    ix->q_prep_rows = (int64_t)nq * TC_T;
   }
   TcParams P{};
   P.centroids_h = ix->centroids_h; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;
@@ -758,6 +767,7 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   P.ring_bytes = (int)ring; P.long_limit = (int)long_limit;
   P.qprep = ix->q_prep.as<uint8_t>(); P.bitmap = d_bitmap; P.list_off = d_list_off; P.cursors = d_cursors; P.pairs = d_pairs;
   P.pid_list = ix->tc_active_list; P.n_list = ix->tc_active_n;
+  P.q_flag = ix->q_flag.as<int>();
   if (P.pid_list && P.n_list == 0) return CB_OK;
   int64_t grid = ix->sm_count;
   const int64_t n_items = P.pid_list ? P.n_list : ix->Np;
@@ -772,7 +782,6 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   else CB_TC_LAUNCH(4);
 #undef CB_TC_LAUNCH
   CB_LAUNCH_CHECK();
-  ix->st_tc_pairs = ix->st_pairs;
 
   // passages longer than the kernel takes: generic kernel on just those
   if (ix->max_doclen > long_limit) {

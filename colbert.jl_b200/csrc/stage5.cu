@@ -132,7 +132,7 @@ int32_t cb_stage5_topk_lens(const uint64_t* d_pairs, const int64_t* d_list_off, 
 // order.  One CTA per query; bitonic sort of (orderable score, ~pid) pairs in shared memory.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_merge_topk(int n_lists, int nq, int k, int npow2, const int64_t* __restrict__ pids,
+k_merge_topk(int n_lists, int nq, int k, int k_out, int npow2, const int64_t* __restrict__ pids,
              const float* __restrict__ scores, int64_t* __restrict__ out_pids, float* __restrict__ out_scores) {
   extern __shared__ uint64_t s_a[];   // npow2 x orderable score (0 = empty)
   uint64_t* s_b = s_a + npow2;        // npow2 x ~pid (larger = smaller pid)
@@ -164,10 +164,10 @@ k_merge_topk(int n_lists, int nq, int k, int npow2, const int64_t* __restrict__ 
     }
   }
   __syncthreads();
-  for (int i = tid; i < k; i += nth) {
+  for (int i = tid; i < k_out; i += nth) {
     const bool ok = i < npow2 && s_b[i] != 0ull;
-    out_scores[(int64_t)q * k + i] = ok ? cb_unorderable((uint32_t)s_a[i]) : -INFINITY;
-    out_pids[(int64_t)q * k + i] = ok ? (int64_t)(~s_b[i]) : 0;
+    out_scores[(int64_t)q * k_out + i] = ok ? cb_unorderable((uint32_t)s_a[i]) : -INFINITY;
+    out_pids[(int64_t)q * k_out + i] = ok ? (int64_t)(~s_b[i]) : 0;
   }
 }
 
@@ -182,7 +182,7 @@ extern "C" int32_t cb_merge_topk_device(int32_t device, int32_t n_lists, int32_t
   const int np = pow2_at_least(n_lists * k);
   const size_t smem = sizeof(uint64_t) * np * 2;
   CB_CUDA(cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_merge_topk<<<nq, 256, smem, (cudaStream_t)stream>>>(n_lists, nq, k, np, d_pids, d_scores, d_out_pids, d_out_scores);
+  k_merge_topk<<<nq, 256, smem, (cudaStream_t)stream>>>(n_lists, nq, k, k, np, d_pids, d_scores, d_out_pids, d_out_scores);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }
@@ -207,5 +207,59 @@ extern "C" int32_t cb_merge_topk(int32_t device, int32_t n_lists, int32_t nq, in
   CB_TRY(cb_merge_topk_device(device, n_lists, nq, k, d_p, d_s, d_op, d_os, nullptr));
   CB_CUDA(cudaMemcpy(out_pids, d_op, n_out * 8, cudaMemcpyDeviceToHost));
   CB_CUDA(cudaMemcpy(out_scores, d_os, n_out * 4, cudaMemcpyDeviceToHost));
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// final ranking on exact fp32 scores.  The tcgen05 scoring kernel's scores carry ~1e-4 relative error
+// (fp16 operands), enough to reorder near-equal passages and to move the k-th boundary against the
+// reference's fp32 `sortperm(scores, rev = true)[1:k]` (src/searching.jl:125-127).  So stage 5 selects the
+// best K2 = max(2k, k + 16) candidates by tensor-core score, those few pairs are re-scored in exact fp32
+// (k_rescore_pairs = the arithmetic of cb_score_pids) and the final (score desc, pid asc) order -- the
+// reference's stable sort over ascending pids -- is decided on the exact scores.  A query whose K2-th
+// tensor-core score is within the error band of its k-th exact score could in principle have lost a
+// member of its top-k to the cut: such queries are counted (stat "rescore_unsafe"; 0 in every run so far).
+// ---------------------------------------------------------------------------------------------
+int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, int K2, float* d_scores_out,
+                                 cudaStream_t st);   // stage34_generic.cu
+
+__global__ void k_rescore_guard(const float* __restrict__ approx, const float* __restrict__ exact_sorted, const int64_t* __restrict__ list_off,
+                                const int32_t* __restrict__ lens, int nq, int K2, int k, unsigned long long* __restrict__ stat_unsafe) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int64_t n = lens ? (int64_t)lens[q] : list_off[q + 1] - list_off[q];
+  if (n <= K2) return;                                   // nothing was cut
+  const float kth = exact_sorted[(int64_t)q * k + (k - 1)];
+  const float cut = approx[(int64_t)q * K2 + (K2 - 1)];   // every cut candidate has a tensor-core score <= this
+  if (!(kth - cut > 2.5e-4f * fabsf(kth))) atomicAdd(stat_unsafe, 1ULL);
+}
+
+int32_t cb_final_topk(cb_index* ix, const float* dQ, int nq, int T, int k, const uint64_t* d_pairs, const int64_t* d_list_off,
+                      const int32_t* d_lens, int64_t* d_out_pids, float* d_out_scores, cudaStream_t st) {
+  CB_REQUIRE(k >= 1 && k <= CB_MAX_K, CB_ERR_UNSUPPORTED, "k must be in 1..%d (got %d)", CB_MAX_K, k);
+  if (nq == 0) return CB_OK;
+  int K2 = 2 * k > k + 16 ? 2 * k : k + 16;
+  if (K2 > CB_MAX_K) K2 = CB_MAX_K;
+  if (!ix->opt_exact_rescore || !ix->stats_tc_selected) {   // the generic kernel's scores are already the exact ones
+    const int kp = pow2_at_least(k);
+    k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, d_lens, k, kp, ix->pid_base, d_out_pids, d_out_scores);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+  }
+  CB_TRY(ix->fin_pids.ensure(sizeof(int64_t) * (size_t)nq * K2));
+  CB_TRY(ix->fin_scores.ensure(sizeof(float) * (size_t)nq * K2 * 2));
+  int64_t* f_pids = ix->fin_pids.as<int64_t>();
+  float* f_approx = ix->fin_scores.as<float>();
+  float* f_exact = f_approx + (size_t)nq * K2;
+  const int kp = pow2_at_least(K2);
+  k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, d_lens, K2, kp, ix->pid_base, f_pids, f_approx);
+  CB_LAUNCH_CHECK();
+  CB_TRY(cb_generic_rescore_pairs(ix, dQ, nq, T, f_pids, K2, f_exact, st));
+  const size_t smem = sizeof(uint64_t) * kp * 2;
+  CB_CUDA(cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_merge_topk<<<nq, 256, smem, st>>>(1, nq, K2, k, kp, f_pids, f_exact, d_out_pids, d_out_scores);
+  CB_LAUNCH_CHECK();
+  k_rescore_guard<<<(nq + 255) / 256, 256, 0, st>>>(f_approx, d_out_scores, d_list_off, d_lens, nq, K2, k, cb_stats_dev(ix) + 5);
+  CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -169,6 +169,18 @@ class Searcher:
         L.check(L.load().cb_search_batch_device(self._h, q_ptr, nq, T, nprobe, k, out_pids_ptr, out_scores_ptr,
                                                 out_counts_ptr, stream))
 
+    def probe_device(self, q_ptr, nq, T, out_cells_ptr, stream=None, nprobe=None):
+        """Stage 1 alone on device buffers: int32 cells [nq][T][nprobe] (1-based, 0 = none)."""
+        nprobe = self.config.nprobe if nprobe is None else nprobe
+        L.check(L.load().cb_probe_device(self._h, q_ptr, nq, T, nprobe, out_cells_ptr, stream))
+
+    def search_batch_cells_device(self, q_ptr, cells_ptr, nq, T, k, out_pids_ptr, out_scores_ptr, out_counts_ptr,
+                                  stream=None, nprobe=None):
+        """`search_batch_device` with the stage-1 cells supplied by the caller (see `probe_device`)."""
+        nprobe = self.config.nprobe if nprobe is None else nprobe
+        L.check(L.load().cb_search_batch_cells_device(self._h, q_ptr, cells_ptr, nq, T, nprobe, k, out_pids_ptr,
+                                                      out_scores_ptr, out_counts_ptr, stream))
+
     def search_batch_plaid(self, Q, k: int, ncells: int = 4, centroid_score_threshold: float = 0.4, ndocs: int = 1000):
         """PLAID-style pruned search (BASELINE config 5; no reference counterpart, semantics in
         oracle.plaid_search): candidates from `ncells` cells per token, centroid-score threshold

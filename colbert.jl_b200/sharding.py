@@ -3,10 +3,12 @@
 The reference is single-process, single-device (src/infra/config.jl:57-58: `rank`/`nranks` exist
 but are not used at search time).  Passages are independent in every stage after stage 1, so the
 index shards by contiguous passage range, balanced by embedding count; each rank scores its own
-shard for the same queries (stage 1 is replicated: cheaper than exchanging its output) and the
-ONLY exchange is the per-shard top-k lists -- nq * k * 12 bytes per rank -- which are all-gathered
-and merged by (score desc, pid asc), the order of the reference's stable `sortperm` over ascending
-pids (src/searching.jl:125-127).
+shard for the same queries.  Stage 1 (query tokens x centroids) depends on the queries only and every
+shard holds the same centroids, so it is split by QUERY instead: rank r probes queries
+[r nq/N, (r+1) nq/N) and the ranks all-gather the cells (nq * T * nprobe int32 = 256 KB per batch);
+replicated on every rank it was a third of the 8-GPU step (round 1).  The other exchange is the per-shard
+top-k lists -- nq * k * 12 bytes per rank -- all-gathered and merged by (score desc, pid asc), the order of
+the reference's stable `sortperm` over ascending pids (src/searching.jl:125-127).
 
 This module is host-side plumbing only: the scoring and the merge run in libcolbert_b200.so; the
 exchange is `torch.distributed` (NCCL over NVLink on GPUs; the same code runs on the `gloo` backend
@@ -60,16 +62,35 @@ def gather_topk(pids, scores, group=None):
     return all_p.view(world, nq, k), all_s.view(world, nq, k)
 
 
+def query_slice(nq: int, world: int, rank: int):
+    """Queries [lo, hi) whose stage 1 rank `rank` computes, and the common padded slice length."""
+    per = (nq + world - 1) // world
+    lo = min(nq, rank * per)
+    return lo, min(nq, lo + per), per
+
+
+def gather_cells(cells_all, per: int, rank: int, group=None):
+    """All-gathers the stage-1 cells: `cells_all` int32 [world * per][T][nprobe] whose rows
+    [rank * per, (rank + 1) * per) this rank has filled; on return every rank holds all rows."""
+    import torch.distributed as dist
+    mine = cells_all[rank * per:(rank + 1) * per]
+    dist.all_gather_into_tensor(cells_all.view(-1), mine.reshape(-1).clone() if cells_all.device.type == "cpu" else mine.view(-1), group=group)
+    return cells_all
+
+
 class ShardedSearcher:
     """One rank's view of a passage-sharded index: `searcher` holds this rank's shard (created with
     pid_base = first passage of the shard, so its pids are already global)."""
 
-    def __init__(self, searcher, group=None, merge=None):
+    def __init__(self, searcher, group=None, merge=None, shard_stage1=True):
         import torch.distributed as dist
         self.searcher = searcher
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._merge = merge   # injected by the CPU (gloo) tests; None = cb_merge_topk_device
+        self.shard_stage1 = shard_stage1
+        self._cells = None
 
     def merge(self, all_p, all_s, out_p, out_s, stream=None):
         if self._merge is not None:
@@ -91,7 +112,18 @@ class ShardedSearcher:
         nq, T, _ = Qd.shape
 
         def local(p, s_):
-            if plaid is None:
+            if plaid is None and self.world > 1 and self.shard_stage1:
+                # stage 1 split by query: probe my slice, all-gather the cells, search with the cells given
+                nprobe = self.searcher.config.nprobe
+                lo, hi, per = query_slice(nq, self.world, self.rank)
+                if self._cells is None or tuple(self._cells.shape) != (self.world * per, T, nprobe):
+                    self._cells = torch.zeros((self.world * per, T, nprobe), dtype=torch.int32, device=Qd.device)
+                if hi > lo:
+                    self.searcher.probe_device(Qd[lo:hi].data_ptr(), hi - lo, T, self._cells[lo:hi].data_ptr(), stream=stream)
+                gather_cells(self._cells, per, self.rank, self.group)
+                self.searcher.search_batch_cells_device(Qd.data_ptr(), self._cells.data_ptr(), nq, T, k, p.data_ptr(),
+                                                        s_.data_ptr(), out_c.data_ptr(), stream=stream)
+            elif plaid is None:
                 self.searcher.search_batch_device(Qd.data_ptr(), nq, T, k, p.data_ptr(), s_.data_ptr(), out_c.data_ptr(),
                                                   stream=stream)
             else:

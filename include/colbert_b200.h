@@ -84,7 +84,10 @@ int32_t cb_index_info(const cb_index* index, int64_t info[8]);
  * Tuning / test knobs.  Keys: "force_generic" (1 = use only the generic SIMT scoring kernel),
  * "stage1_impl" (0 = auto, 1 = SIMT fp32, 2 = tcgen05), "profile" (1 = record per-stage CUDA
  * event timings, readable through cb_get_stat), "tc_astages" (query-tile pipeline stages of the
- * tcgen05 scoring kernel, 2..6; 0 = default).  Unknown key -> CB_ERR_BAD_ARG.
+ * tcgen05 scoring kernel, 2..6; 0 = default), "sync_pairs" (1 = size the pair list exactly with a
+ * host round trip instead of the IVF bound), "exact_rescore" (default 1: the final top-k is decided
+ * on exact fp32 scores of the best max(2k, k+16) tensor-core candidates; 0 = rank by tensor-core
+ * score).  Unknown key -> CB_ERR_BAD_ARG.
  */
 int32_t cb_set_option(cb_index* index, const char* key, int64_t value);
 
@@ -94,7 +97,10 @@ int32_t cb_set_option(cb_index* index, const char* key, int64_t value);
  * "flagged_rows" (query tokens whose top-nprobe needed the exact full scan),
  * "ms_stage1", "ms_stage2", "ms_stage34", "ms_stage5", "ms_total" (need option "profile"),
  * "tc_pairs" / "generic_pairs" (pairs scored by the tcgen05 / the generic kernel),
- * "stage1_tc_rows" (query tokens whose centroid shortlist came from the tcgen05 stage-1 kernel).
+ * "stage1_tc_rows" (query tokens whose centroid shortlist came from the tcgen05 stage-1 kernel),
+ * "rescore_unsafe" (queries whose exact re-score margin could not rule out a missed candidate),
+ * "bad_cells" (caller-supplied cells outside 0:K), "max_cell_len" (longest IVF cell).
+ * Reading a counter of an asynchronous (device) search waits for that batch to finish.
  */
 int32_t cb_get_stat(const cb_index* index, const char* key, double* value);
 
@@ -116,11 +122,27 @@ int32_t cb_search_batch(cb_index* index, const float* Q, int32_t nq, int32_t T, 
 
 /* Same, with Q and the three outputs already in device memory of the index's GPU and all work
  * enqueued on `stream` (a cudaStream_t; NULL = default stream).  Returns after enqueueing the
- * last kernel; the caller synchronises the stream.  (One internal stream sync happens between
- * candidate generation and scoring to size the pair list.) */
+ * last kernel; the caller synchronises the stream.  The batch is a pure stream of launches: no
+ * host round trip inside (the pair list is sized from an IVF bound, flagged stage-1 rows and
+ * out-of-range query batches are routed on the device, counters are read lazily by cb_get_stat). */
 int32_t cb_search_batch_device(cb_index* index, const float* dQ, int32_t nq, int32_t T,
                                int32_t nprobe, int32_t k, int64_t* d_out_pids,
                                float* d_out_scores, int32_t* d_out_counts, void* stream);
+
+/* Stage 1 alone, device-resident (the piece a passage-sharded deployment splits by QUERY: every shard holds
+ * the same centroids, so rank r probes queries [r nq/N, (r+1) nq/N) and the ranks exchange the cells):
+ * `_topk(Q' * centroids, nprobe, dims = 2)` (src/search/ranking.jl:27-31, src/utils.jl:327-332).
+ *   dQ device float[nq][T][dim]; d_out_cells device int32[nq][T][nprobe], 1-based centroid ids, best first
+ *   (0 = none: fewer than nprobe centroids exist).  Enqueued on `stream`. */
+int32_t cb_probe_device(cb_index* index, const float* dQ, int32_t nq, int32_t T, int32_t nprobe,
+                        int32_t* d_out_cells, void* stream);
+
+/* cb_search_batch_device with stage 1 supplied by the caller: d_cells device int32[nq][T][nprobe] as written by
+ * cb_probe_device (on this or any other shard of the same index).  Entries outside 0:K are ignored and counted
+ * (stat "bad_cells"). */
+int32_t cb_search_batch_cells_device(cb_index* index, const float* dQ, const int32_t* d_cells, int32_t nq,
+                                     int32_t T, int32_t nprobe, int32_t k, int64_t* d_out_pids,
+                                     float* d_out_scores, int32_t* d_out_counts, void* stream);
 
 /* PLAID-style pruned search (BASELINE.json config 5).  NOT a reference function: ColBERT.jl lists PLAID
  * pruning as roadmap (README.md:187); the semantics are defined by oracle/oracle.py `plaid_search`

@@ -113,6 +113,15 @@ def _worker(rank, world, port, ret):
         gathered = [torch.zeros_like(out_p) for _ in range(world)]
         dist.all_gather(gathered, out_p)
         assert all(torch.equal(g, out_p) for g in gathered)
+        # stage 1 split by query: every rank probes its query slice, the cells are all-gathered
+        nq, T, nprobe = 7, 4, 2                                    # nq not a multiple of the world size
+        lo_q, hi_q, per = SH.query_slice(nq, world, rank)
+        assert (lo_q, hi_q, per) == ((0, 4, 4) if rank == 0 else (4, 7, 4))
+        truth = torch.arange(world * per * T * nprobe, dtype=torch.int32).view(world * per, T, nprobe)
+        cells = torch.zeros_like(truth)
+        cells[rank * per:(rank + 1) * per] = truth[rank * per:(rank + 1) * per]
+        SH.gather_cells(cells, per, rank)
+        assert torch.equal(cells, truth)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
