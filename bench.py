@@ -38,6 +38,9 @@ WORKLOADS = {
 BLOCK = 32768  # passages per generation block: the global index is identical for every N
 
 
+EXTRA_CONFIGS = ["B", "C_nbits1", "C_nbits4", "C_clustered", "C_plaid"]   # the other BASELINE.json configs, N = 1 only
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -53,6 +56,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true", help="score with the generic SIMT kernel only")
     ap.add_argument("--opt", action="append", default=[], help="library tuning knob key=value (cb_set_option), repeatable")
+    ap.add_argument("--profile", default="uniform", choices=["uniform", "clustered"], help="code profile of the synthetic index (SURVEY 8d)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the legs for the other BASELINE configs (N = 1)")
+    ap.add_argument("--extra", default=",".join(EXTRA_CONFIGS), help="comma-separated subset of " + ",".join(EXTRA_CONFIGS))
+    ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--extra-workload", default=None, choices=sorted(WORKLOADS), help="(debug) run the extra legs on this workload size")
+    ap.add_argument("--no-gate", action="store_true", help="skip the all-query parity gate")
     return ap.parse_args()
 
 
@@ -78,8 +87,10 @@ def shard_bounds(torch, csum, n):
     return SH.shard_bounds(csum.cpu().numpy(), n)
 
 
-def gen_shard(torch, wl, dev, csum, lo, hi, nbits):
-    """codes (int32 holding 1-based ids) and residual bytes of passages [lo, hi)."""
+def gen_shard(torch, wl, dev, csum, lo, hi, nbits, profile="uniform"):
+    """codes (int32 holding 1-based ids) and residual bytes of passages [lo, hi).
+    profile "clustered" (secondary): each passage draws 8 home centroids and 85 % of its tokens
+    come from them (mimics the fan-out of a real collection); "uniform" is the worst-case headline."""
     R = 128 // 8 * nbits
     e_lo, e_hi = int(csum[lo]), int(csum[hi])
     codes = torch.empty(e_hi - e_lo, dtype=torch.int32, device=dev)
@@ -90,6 +101,13 @@ def gen_shard(torch, wl, dev, csum, lo, hi, nbits):
         b0, b1 = int(csum[p0]), int(csum[p1])
         g.manual_seed(1003_000_000 + b)
         cb_ = torch.randint(1, wl["K"] + 1, (b1 - b0,), generator=g, device=dev, dtype=torch.int32)
+        if profile == "clustered":
+            npass = p1 - p0
+            home = torch.randint(1, wl["K"] + 1, (npass, 8), generator=g, device=dev, dtype=torch.int32)
+            pid_of = torch.repeat_interleave(torch.arange(npass, device=dev), csum[p0 + 1:p1 + 1] - csum[p0:p1])
+            pick = home[pid_of, torch.randint(0, 8, (b1 - b0,), generator=g, device=dev)]
+            cb_ = torch.where(torch.rand((b1 - b0,), generator=g, device=dev) < 0.85, pick, cb_)
+            del home, pid_of, pick
         g.manual_seed(1004_000_000 + b)
         rb = torch.randint(0, 256, (b1 - b0, R), generator=g, device=dev, dtype=torch.uint8)
         s0, s1 = max(b0, e_lo), min(b1, e_hi)
@@ -200,6 +218,212 @@ def emit(line):
     out.flush()
 
 
+def digest(*tensors):
+    """sha1 over the raw bytes of the result tensors: equal digests <=> bit-identical results."""
+    import hashlib
+    h = hashlib.sha1()
+    for t in tensors:
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def all_query_gate(torch, s, Qd, out_p, out_s, out_c, k, nprobe, lo, hi, full=True):
+    """Parity gate over ALL queries of the batch (seconds, not the 15 s/query of the CPU oracle):
+      * every returned (pid, score) whose passage lives on this shard is re-scored by cb_score_pids -- the exact
+        fp32 generic kernel, itself oracle-checked in tests/ -- and must match bit for bit;
+      * order: scores non-increasing, equal scores in ascending pid (the reference's stable sortperm)."""
+    P, Sc = out_p.cpu().numpy(), out_s.cpu().numpy()
+    Qh = Qd.cpu().numpy()
+    nq = P.shape[0]
+    bad_score = bad_order = checked = 0
+    step = 1 if full else 16
+    for q in range(0, nq, step):
+        mine = (P[q] > lo) & (P[q] <= hi)
+        if mine.any():
+            ex = s.score_pids(Qh[q].T, P[q][mine])
+            checked += int(mine.sum())
+            bad_score += int(np.sum(ex != Sc[q][mine]))
+        valid = P[q] > 0
+        sc, pp = Sc[q][valid], P[q][valid]
+        if len(sc) > 1:
+            d = np.diff(sc)
+            bad_order += int(np.sum(d > 0) + np.sum((d == 0) & (np.diff(pp) < 0)))
+    return {"queries": len(range(0, nq, step)), "pairs_rescored_exact_fp32": checked, "score_mismatches": bad_score,
+            "order_violations": bad_order}
+
+
+def retrieve_count_gate(s, Qd, out_c, nprobe, every):
+    """cb_retrieve (stages 1+2 for one query, bit-exact vs the oracle in tests/) must give the batch's candidate counts."""
+    import ctypes as C
+    import colbert_jl_b200 as cb
+    lib = cb.load()
+    Qh, C_ = Qd.cpu().numpy(), out_c.cpu().numpy()
+    bad = n = 0
+    cnt = C.c_int64()
+    for q in range(0, Qh.shape[0], every):
+        qc = np.ascontiguousarray(Qh[q])
+        cb._lib.check(lib.cb_retrieve(s._h, qc.ctypes.data_as(C.c_void_p), Qh.shape[1], nprobe, None, 0, C.byref(cnt)))
+        bad += int(cnt.value != C_[q])
+        n += 1
+    return {"queries": n, "count_mismatches": bad}
+
+
+class Leg:
+    """One workload on this rank's shard: index generation, searcher, timed steps, per-stage profile, gates."""
+
+    def __init__(self, torch, cb, args, wl_key, nbits, profile, nprobe, k, rank, world, local, dist):
+        self.torch, self.cb, self.args = torch, cb, args
+        self.wl, self.nbits, self.profile, self.nprobe, self.k = WORKLOADS[wl_key], nbits, profile, nprobe, k
+        self.rank, self.world, self.dist = rank, world, dist
+        self.dev = torch.device("cuda", local)
+        self.local = local
+        wl = self.wl
+        self.cen, self.doclens, self.csum = gen_global(torch, wl, self.dev)
+        bounds = shard_bounds(torch, self.csum, world)
+        self.lo, self.hi = bounds[rank], bounds[rank + 1]
+        self.codes, self.res = gen_shard(torch, wl, self.dev, self.csum, self.lo, self.hi, nbits, profile)
+        self.Qd = gen_queries(torch, self.cen, args.nq, 32, nprobe, self.dev)
+        self.w = torch.from_numpy(bucket_weights(nbits)).to(self.dev)
+        dl = self.doclens[self.lo:self.hi].contiguous()
+        self.ne_local = self.codes.numel()
+        cfg = cb.ColBERTConfig(dim=128, nbits=nbits, nprobe=nprobe, query_maxlen=32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.s = cb.Searcher.from_device(cfg, wl["K"], self.hi - self.lo, self.codes.numel(), self.cen.data_ptr(), self.w.data_ptr(),
+                                         self.codes.data_ptr(), self.res.data_ptr(), dl.data_ptr(), None, None, device=local,
+                                         pid_base=self.lo)
+        self.t_build = time.perf_counter() - t0
+        if args.force_generic:
+            self.s.set_option("force_generic", 1)
+        for kv in args.opt:
+            key, val = kv.split("=")
+            self.s.set_option(key, int(val))
+        nq = args.nq
+        self.out_p = torch.zeros((nq, k), dtype=torch.int64, device=self.dev)
+        self.out_s = torch.zeros((nq, k), dtype=torch.float32, device=self.dev)
+        self.out_c = torch.zeros((nq,), dtype=torch.int32, device=self.dev)
+        from colbert_jl_b200 import sharding as SH
+        self.sharded = SH.ShardedSearcher(self.s)
+        self.loc_p, self.loc_s = torch.zeros_like(self.out_p), torch.zeros_like(self.out_s)
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def drop_host_copies(self):
+        self.codes = self.res = None
+        self.torch.cuda.empty_cache()
+
+    def close(self):
+        self.s.close()
+        for a in ("cen", "doclens", "csum", "codes", "res", "Qd", "out_p", "out_s", "out_c", "loc_p", "loc_s", "sharded", "s"):
+            setattr(self, a, None)
+        self.torch.cuda.empty_cache()
+
+    def step(self, plaid=None, Q=None):
+        self.sharded.search_batch_device(self.Qd if Q is None else Q, self.k, self.out_p, self.out_s, self.out_c, stream=self.stream,
+                                         local_p=self.loc_p, local_s=self.loc_s, plaid=plaid)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, steps, warmup, plaid=None, sample_clocks=False):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step(plaid)
+        self.barrier()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(self.local)
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(plaid)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        return float(ms.item()) / steps, clocks
+
+    def stage_profile(self, nprof=3):
+        """per-stage CUDA events on the launching stream (cb_set_option("profile")), this rank's shard"""
+        s, torch = self.s, self.torch
+        s.set_option("profile", 1)
+        prof = {"ms_stage1": 0.0, "ms_stage2": 0.0, "ms_stage34": 0.0, "ms_stage5": 0.0, "ms_total": 0.0}
+        for _ in range(nprof):
+            s.search_batch_device(self.Qd.data_ptr(), self.args.nq, 32, self.k, self.loc_p.data_ptr(), self.loc_s.data_ptr(),
+                                  self.out_c.data_ptr(), stream=self.stream)
+            torch.cuda.synchronize()
+            for key in prof:
+                prof[key] += s.stat(key) / nprof
+        s.set_option("profile", 0)
+        return prof
+
+    def roofline(self, prof, pairs, pair_embs, workload_key):
+        """HBM-equivalent roofline of the dominant kernel (algorithmic bytes / kernel time / measured copy
+        bandwidth) first; the tensor and L2 -> SM views of the same launch beside it."""
+        args = self.args
+        pk = peaks()
+        R = 128 // 8 * self.nbits
+        T, dim, nq, k = 32, 128, args.nq, self.k
+        flops = 2.0 * T * dim * pair_embs                      # 8192 flop per (query, candidate embedding)
+        alg_bytes = pair_embs * (4 + R) + pairs * 16 + nq * k * 12
+        t34 = prof["ms_stage34"] * 1e-3
+        gbs = alg_bytes / t34 / 1e9 if t34 > 0 else 0.0
+        tf = flops / t34 / 1e12 if t34 > 0 else 0.0
+        traffic = None    # dram__bytes_read + write of one launch, from the committed ncu --set full capture of this workload
+        for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if traffic is None and os.path.exists(tpath) and self.world == 1 and not args.force_generic and self.profile == "uniform":
+                traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(f"{workload_key}:nbits={self.nbits}")
+        l2_bytes = pairs * 8192.0 + self.ne_local * (256.0 + 4 + R)
+        return {"kernel": "k_maxsim_tc (fused decompress + MaxSim, tcgen05)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
+                "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
+                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"] + ", STREAM-style copy",
+                "note": "algorithmic bytes = (4 + R) B x pair embeddings + 16 B x pairs (SURVEY 8d); the packed index itself streams "
+                        "from DRAM once per batch (passage-major), so real DRAM traffic is far below this",
+                "tensor": {"achieved": tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"],
+                           "peak_source": "sustained bf16 cuBLAS (fp16 and bf16 share the tcgen05 rate)"},
+                "l2_to_sm": {"bytes_per_launch": l2_bytes, "achieved": l2_bytes / t34 / 1e9 if t34 > 0 else 0.0, "unit": "GB/s",
+                             "measured_chip_ceiling": 22200.0, "one_issuing_warp_8KB_copies": 8890.0,
+                             "note": "8 KB query tile per pair + 292 B per indexed embedding; ceilings measured by "
+                                     "tools/l2_to_sm_ceiling.cu (profiles/r02_l2_to_sm_ceiling.txt); the kernel is bound by the "
+                                     "shared-memory / L1 data pipe (TMA writes + UMMA operand reads + LSU), DESIGN.md section 4"},
+                "stage_ms": prof, "pairs_per_step": pairs, "pair_embeddings_per_step": pair_embs}
+
+
+def plaid_oracle_gate(torch, leg, knobs, nqc):
+    """BASELINE config 5 has no reference implementation (README.md:187): the semantics are the oracle's own
+    (oracle.plaid_search), so this gate is labelled parity-UNPINNED."""
+    from oracle import oracle as O
+    oix = host_oracle_index(torch, leg.wl, leg.nbits, leg.cen, leg.doclens, leg.codes, leg.res, knobs["ncells"])
+    gp, gs, gc = leg.out_p.cpu().numpy(), leg.out_s.cpu().numpy(), leg.out_c.cpu().numpy()
+    Qh = leg.Qd[:nqc].cpu().numpy()
+    ok_set = ok_sel = True
+    max_rel, nswap, nswap_beyond_noise = 0.0, 0, 0
+    for q in range(nqc):
+        op, osc, sel, cand, approx = O.plaid_search(oix, Qh[q].T, leg.k, knobs["ncells"], knobs["centroid_score_threshold"],
+                                                    knobs["ndocs"], return_selected=True)
+        kk = len(op)
+        ok_set &= set(gp[q, :kk].tolist()) == set(op.tolist())
+        ok_sel &= bool(gc[q] == len(sel)) and set(gp[q, :kk].tolist()) <= set(sel.tolist())
+        max_rel = max(max_rel, float(np.max(np.abs(gs[q, :kk] - osc) / np.abs(osc))))
+        oscore = dict(zip(op.tolist(), osc.tolist()))
+        for i in np.nonzero(gp[q, :kk] != op)[0]:
+            nswap += 1
+            a = oscore.get(int(gp[q, i]))
+            # float noise between two fp32 summation orders: 32 x 128 terms ~ 1e-5 relative
+            nswap_beyond_noise += int(a is None or abs(a - float(osc[i])) > 1e-5 * abs(float(osc[i])))
+    return {"pinned": False, "why": "no reference implementation of PLAID pruning exists (README.md:187); semantics = oracle.plaid_search",
+            "queries_checked": nqc, "topk_sets_identical": bool(ok_set), "selection_counts_identical": bool(ok_sel),
+            "order_differences": nswap, "order_differences_beyond_fp32_noise": nswap_beyond_noise,
+            "max_rel_score_err": max_rel, "tolerance": 1e-3}
+
+
 def main():
     # Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there when
     # NCCL_DEBUG is set): keep the original stdout for the JSON line only and point fd 1 at stderr.
@@ -216,15 +440,17 @@ def main():
     T, dim, nq, k = 32, 128, args.nq, args.k
     cfg_out = {"workload": wl["name"] + f", nbits={args.nbits}", "passages": wl["passages"], "centroids": wl["K"],
                "nbits": args.nbits, "queries_per_step": nq, "query_tokens": T, "dim": dim, "k": k, "nprobe": args.nprobe,
-               "code_profile": "uniform", "sharding": f"passage-range x{world}",
-               "l2_policy": "inputs (packed index, GBs) are far larger than the 126 MB L2; no flush needed"}
+               "code_profile": args.profile, "sharding": f"passage-range x{world}",
+               "l2_policy": "inputs (packed index, GBs) are far larger than the 126 MB L2; no flush needed",
+               "generator": "torch Philox streams on the device (seeds 1001-1004 / 2001, SURVEY 8d distributions); the unit tests use "
+                            "the numpy PCG64 twin in colbert.jl_b200/synthetic.py: same distributions, different streams"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
         cen, doclens, csum = gen_global(torch, wl, dev)
-        codes, res = gen_shard(torch, wl, dev, csum, 0, wl["passages"], args.nbits)
+        codes, res = gen_shard(torch, wl, dev, csum, 0, wl["passages"], args.nbits, args.profile)
         Qd = gen_queries(torch, cen, max(8, args.steps + args.warmup), T, args.nprobe, dev)
         oix = host_oracle_index(torch, wl, args.nbits, cen, doclens, codes, res, args.nprobe)
         Qh = Qd.cpu().numpy()
@@ -256,67 +482,21 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    cen, doclens, csum = gen_global(torch, wl, dev)
-    bounds = shard_bounds(torch, csum, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
-    codes, res = gen_shard(torch, wl, dev, csum, lo, hi, args.nbits)
-    Qd = gen_queries(torch, cen, nq, T, args.nprobe, dev)
-    w = torch.from_numpy(bucket_weights(args.nbits)).to(dev)
-    dl = doclens[lo:hi].contiguous()
-    ne_local = codes.numel()
-    cfg = cb.ColBERTConfig(dim=dim, nbits=args.nbits, nprobe=args.nprobe, query_maxlen=T)
-    torch.cuda.synchronize()
-    t_build = time.perf_counter()
-    s = cb.Searcher.from_device(cfg, wl["K"], hi - lo, codes.numel(), cen.data_ptr(), w.data_ptr(), codes.data_ptr(),
-                                res.data_ptr(), dl.data_ptr(), None, None, device=local, pid_base=lo)
-    t_build = time.perf_counter() - t_build
-    if args.force_generic:
-        s.set_option("force_generic", 1)
-    for kv in args.opt:
-        key, val = kv.split("=")
-        s.set_option(key, int(val))
+    leg = Leg(torch, cb, args, args.workload, args.nbits, args.profile, args.nprobe, k, rank, world, local, dist)
+    s, Qd, out_p, out_s, out_c = leg.s, leg.Qd, leg.out_p, leg.out_s, leg.out_c
     keep_for_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
     if not keep_for_cpu:
-        del codes, res
-        torch.cuda.empty_cache()
-
-    out_p = torch.zeros((nq, k), dtype=torch.int64, device=dev)
-    out_s = torch.zeros((nq, k), dtype=torch.float32, device=dev)
-    out_c = torch.zeros((nq,), dtype=torch.int32, device=dev)
-    from colbert_jl_b200 import sharding as SH
-    sharded = SH.ShardedSearcher(s)
-    loc_p, loc_s = torch.zeros_like(out_p), torch.zeros_like(out_s)   # per-shard lists (world > 1)
+        leg.drop_host_copies()
     lib = cb.load()
-    stream = torch.cuda.current_stream().cuda_stream
+    t_build = leg.t_build
 
-    def step():   # world > 1: local search, all-gather of the per-shard top-k lists (NCCL), merge kernel
-        sharded.search_batch_device(Qd, k, out_p, out_s, out_c, stream=stream, local_p=loc_p, local_s=loc_s)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop()
-    ms_per_step = float(ms.item()) / args.steps
+    ms_per_step, clocks = leg.timed(args.steps, args.warmup, sample_clocks=True)
     value = nq / (ms_per_step * 1e-3)
-    launches = int(s.stat("launches")) + (1 if world > 1 else 0)
+    # kernels launched by this rank's library per step (+ the all-gathers / merge of the sharded path)
+    launches = int(s.stat("launches")) + (3 if world > 1 else 0)
     pairs, pair_embs = s.stat("pairs"), s.stat("pair_embeddings")
+    flagged, unsafe = s.stat("flagged_rows"), s.stat("rescore_unsafe")
+    result_digest = digest(out_p, out_s)
 
     # ---- end to end: pinned host buffers in, host results out, every step
     Qh = torch.empty((nq, T, dim), dtype=torch.float32, pin_memory=True)
@@ -331,90 +511,133 @@ def main():
             cb._lib.check(lib.cb_search_batch(s._h, Qh.data_ptr(), nq, T, args.nprobe, k, hp.data_ptr(), hs.data_ptr(), hc.data_ptr()))
         else:
             Qd2.copy_(Qh, non_blocking=True)
-            sharded.search_batch_device(Qd2, k, out_p, out_s, out_c, stream=stream, local_p=loc_p, local_s=loc_s)
+            leg.step(Q=Qd2)
             hp.copy_(out_p, non_blocking=True)
             hs.copy_(out_s, non_blocking=True)
             hc.copy_(out_c, non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_step()
-    barrier()
+    leg.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    barrier()
+    leg.barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = nq * args.steps / float(t_e2e.item())
-    if world == 1 and not any(kv.startswith("tc_ablate") for kv in args.opt):   # (ablation runs compute garbage on purpose)
-        assert torch.equal(hp.to(dev), out_p) and torch.equal(hs.to(dev), out_s), "host and device entry points disagree"
+    host_equals_device = bool(torch.equal(hp.to(dev), out_p) and torch.equal(hs.to(dev), out_s))
+    if not any(kv.startswith("tc_ablate") for kv in args.opt):   # (ablation runs compute garbage on purpose)
+        assert host_equals_device, "host and device entry points disagree"
 
     # ---- roofline of the dominant kernel (fused decompress + MaxSim), CUDA events on its stream
-    s.set_option("profile", 1)
-    prof = {"ms_stage1": 0.0, "ms_stage2": 0.0, "ms_stage34": 0.0, "ms_stage5": 0.0, "ms_total": 0.0}
-    nprof = 3
-    for _ in range(nprof):
-        s.search_batch_device(Qd.data_ptr(), nq, T, k, out_p.data_ptr(), out_s.data_ptr(), out_c.data_ptr(), stream=stream)
-        torch.cuda.synchronize()
-        for key in prof:
-            prof[key] += s.stat(key) / nprof
-    s.set_option("profile", 0)
-    pk = peaks()
-    R = dim // 8 * args.nbits
-    flops = 2.0 * T * dim * pair_embs                      # 8192 flop per (query, candidate embedding)
-    alg_bytes = pair_embs * (4 + R) + pairs * 16 + nq * k * 12
-    t34 = prof["ms_stage34"] * 1e-3
-    tf = flops / t34 / 1e12 if t34 > 0 else 0.0
-    traffic = None    # dram__bytes_read + write of one launch, from the committed ncu --set full capture of this workload
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath) and world == 1 and not args.force_generic:
-        traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(f"{args.workload}:nbits={args.nbits}")
-    roofline = {"kernel": "k_maxsim_tc (fused decompress + MaxSim, tcgen05)", "bound": "tensor", "achieved": tf,
-                "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tf / pk["tf_sus"], "traffic": traffic,
-                "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"] +
-                ", sustained bf16 (kernel runs inside a long step; fp16 and bf16 share the tcgen05 rate)",
-                "hbm_equiv": {"achieved": alg_bytes / t34 / 1e9 if t34 > 0 else 0.0, "peak": pk["hbm"], "unit": "GB/s",
-                              "frac": (alg_bytes / t34 / 1e9) / pk["hbm"] if t34 > 0 else 0.0,
-                              "note": "algorithmic bytes (36 B x pair embeddings + 16 B x pairs) / kernel time; real DRAM "
-                                      "traffic is far lower because a passage is decompressed once per batch, not per pair"},
-                "stage_ms": prof, "pairs_per_step": pairs, "pair_embeddings_per_step": pair_embs}
-    # What actually bounds the kernel: every pair pulls its query's 8 KB fp16 tile from L2
-    # into the SM, every indexed embedding its 256 B fp16 centroid row + packed bytes.  Across eight structurally
-    # different builds of the kernel this stream ran at the same ~7.3-8.6 TB/s (ncu l1tex__m_xbar2l1tex_read_bytes
-    # per second), so it is reported next to the HBM / tensor numbers.
-    l2_bytes = pairs * 8192.0 + ne_local * (256.0 + 4 + R)
-    roofline["l2_to_sm"] = {"bytes_per_launch": l2_bytes, "achieved": l2_bytes / t34 / 1e9 if t34 > 0 else 0.0, "unit": "GB/s",
-                            "observed_ceiling": 8700.0,
-                            "note": "8 KB query tile per pair + 292 B per indexed embedding; ceiling = highest "
-                                    "xbar->L1 read rate ncu reported for any build of this kernel (profiles/)"}
+    prof = leg.stage_profile()
+    if world > 1:   # per-rank shard numbers: report the slowest rank's stage times, the job's pair totals
+        tt = torch.tensor([prof[kx] for kx in sorted(prof)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        prof = dict(zip(sorted(prof), [float(x) for x in tt.tolist()]))
+    roofline = leg.roofline(prof, pairs, pair_embs, args.workload)
+    roofline["scope"] = "this rank's shard (stage times = max over ranks)" if world > 1 else "the whole index"
 
-    # ---- CPU baseline (N = 1, rank 0): the oracle on a bounded sample of the same workload, + parity gate
+    # ---- parity at every N: all-query gate on every rank, result digest against the committed N = 1 digest
+    parity = {"digest": result_digest, "tolerance": 1e-3, "stage1_rows_redone_by_exact_scan": flagged, "rescore_unsafe_queries": unsafe,
+              "host_entry_equals_device_entry": host_equals_device}
+    if not args.no_gate:
+        g = all_query_gate(torch, s, Qd, out_p, out_s, out_c, k, args.nprobe, leg.lo, leg.hi)
+        rc = retrieve_count_gate(s, Qd, out_c, args.nprobe, every=4)
+        tt = torch.tensor([g["pairs_rescored_exact_fp32"], g["score_mismatches"], g["order_violations"], rc["queries"],
+                           rc["count_mismatches"]], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            tt[2] //= world   # every rank checks the same (global) lists for order
+        parity["all_query_gate"] = {"queries": nq, "returned_pairs_rescored_exact_fp32": int(tt[0]), "score_mismatches": int(tt[1]),
+                                    "order_violations": int(tt[2]), "retrieve_count_queries_x_shards": int(tt[3]),
+                                    "retrieve_count_mismatches": int(tt[4]),
+                                    "how": "cb_score_pids (exact fp32, oracle-checked in tests/) on every returned pair, bit for bit; "
+                                           "cb_retrieve candidate counts (bit-exact vs the oracle in tests/) on every 4th query per shard"}
+    dpath = os.path.join(ROOT, "profiles", "r02_result_digests.json")
+    dkey = f"{args.workload}:nbits={args.nbits}:profile={args.profile}:nq={nq}:k={k}:nprobe={args.nprobe}"
+    if os.path.exists(dpath):
+        ref_d = json.load(open(dpath)).get(dkey)
+        parity["digest_n1_committed"] = ref_d
+        parity["equals_n1"] = (None if ref_d is None else bool(ref_d == result_digest))
+    parity["digest_key"] = dkey
+
+    # ---- CPU baseline (N = 1, rank 0): the oracle on a bounded sample of the same workload, + oracle parity on that sample
     cpu = None
-    parity = None
     if keep_for_cpu:
-        oix = host_oracle_index(torch, wl, args.nbits, cen, doclens, codes, res, args.nprobe)
-        del codes, res
+        oix = host_oracle_index(torch, wl, args.nbits, leg.cen, leg.doclens, leg.codes, leg.res, args.nprobe)
+        leg.drop_host_copies()
         nqc = args.cpu_queries
         sec, results = time_oracle(oix, Qd[:nqc].cpu().numpy(), k, nqc)
+        del oix
         cpu = {"value": 1.0 / sec, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{nqc} of the {nq} queries over the full index; numpy/OpenBLAS restatement of ColBERT.jl search "
                          f"(Julia absent), BLAS threads = {os.cpu_count()}"}
         gp, gs = out_p[:nqc].cpu().numpy(), out_s[:nqc].cpu().numpy()
         ok_p = all(np.array_equal(gp[q], results[q][0]) for q in range(nqc))
         max_rel = max(float(np.max(np.abs(gs[q] - results[q][1]) / np.abs(results[q][1]))) for q in range(nqc))
-        parity = {"queries_checked": nqc, "topk_pids_identical": bool(ok_p), "max_rel_score_err": max_rel, "tolerance": 1e-3}
+        parity["oracle"] = {"queries_checked": nqc, "topk_pids_identical": bool(ok_p), "max_rel_score_err": max_rel}
+        assert max_rel <= 1e-3, "scores differ from the oracle by more than the 1e-3 tolerance"
+
+    # ---- the other BASELINE.json configs (N = 1): same harness, short runs, same gates
+    configs = None
+    if world == 1 and not args.no_extra:
+        leg.close()
+        del leg, s, Qd, out_p, out_s, out_c
+        torch.cuda.empty_cache()
+        configs = {}
+        plaid_knobs = dict(ncells=4, centroid_score_threshold=0.4, ndocs=1000)
+        spec = {"B": ("B", 2, "uniform", 2, 10, None), "C_nbits1": ("C", 1, "uniform", 2, 10, None),
+                "C_nbits4": ("C", 4, "uniform", 2, 10, None), "C_clustered": ("C", 2, "clustered", 2, 10, None),
+                "C_plaid": ("C", 2, "uniform", 4, 100, plaid_knobs)}
+        for name in [x for x in args.extra.split(",") if x]:
+            wk, nb, profile, nprobe, kk, plaid = spec[name]
+            wk = args.extra_workload or wk
+            t_leg = time.perf_counter()
+            try:
+                lg = Leg(torch, cb, args, wk, nb, profile, nprobe, kk, 0, 1, local, None)
+                ms, _ = lg.timed(args.extra_steps, 3, plaid=plaid)
+                out = {"workload": WORKLOADS[wk]["name"], "nbits": nb, "code_profile": profile, "nprobe": nprobe, "k": kk,
+                       "ms_per_step": ms, "value": nq / (ms * 1e-3), "unit": "queries/s", "steps": args.extra_steps, "warmup": 3,
+                       "digest": digest(lg.out_p, lg.out_s)}
+                if plaid is None:
+                    prs, pes = lg.s.stat("pairs"), lg.s.stat("pair_embeddings")
+                    out["rescore_unsafe_queries"] = lg.s.stat("rescore_unsafe")
+                    rf = lg.roofline(lg.stage_profile(2), prs, pes, wk)
+                    out["hbm_equiv"] = {"achieved": rf["achieved"], "peak": rf["peak"], "unit": "GB/s", "frac": rf["frac"]}
+                    out["tensor_frac"] = rf["tensor"]["frac"]
+                    out["stage_ms"] = rf["stage_ms"]
+                    out["pairs_per_step"], out["pair_embeddings_per_step"] = prs, pes
+                    if not args.no_gate:
+                        out["parity"] = all_query_gate(torch, lg.s, lg.Qd, lg.out_p, lg.out_s, lg.out_c, kk, nprobe, lg.lo, lg.hi, full=False)
+                        out["parity"].update(retrieve_count_gate(lg.s, lg.Qd, lg.out_c, nprobe, every=64))
+                else:
+                    out["plaid"] = dict(plaid_knobs, candidate_pairs=lg.s.stat("plaid_candidates"),
+                                        surviving_query_centroid_pairs=lg.s.stat("plaid_survivors"),
+                                        exactly_rescored_pairs=lg.s.stat("plaid_rescored"))
+                    if not args.no_gate:
+                        out["parity"] = all_query_gate(torch, lg.s, lg.Qd, lg.out_p, lg.out_s, lg.out_c, kk, nprobe, lg.lo, lg.hi, full=False)
+                        if not args.no_cpu_baseline:
+                            out["parity"]["oracle"] = plaid_oracle_gate(torch, lg, plaid_knobs, 1)
+                lg.close()
+                del lg
+            except Exception as ex:  # a leg must never take the headline line down with it
+                out = {"error": f"{type(ex).__name__}: {ex}"}
+            out["leg_wall_s"] = time.perf_counter() - t_leg
+            configs[name] = out
+            torch.cuda.empty_cache()
 
     if rank == 0:
         emit(json.dumps({"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05); f32 exact decisions",
+                          "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05); f32 exact decisions and final scores",
                           "data": "synthetic", "config": cfg_out, "clocks": clocks,
                           "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * T * dim * 4,
                                   "d2h_bytes_per_step": nq * k * 12 + nq * 4},
                           "gpu_launches": launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-                          "index_build_s": t_build}))
+                          "configs": configs, "index_build_s": t_build}))
     if world > 1:
         dist.destroy_process_group()
 

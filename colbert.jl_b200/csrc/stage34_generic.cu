@@ -204,10 +204,10 @@ constexpr int R_THREADS = 128, R_TOK = 16;
 __global__ void __launch_bounds__(R_THREADS)
 k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64_t pid_base, int64_t Np, float* __restrict__ scores_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int dim = P.dim, T = P.T, ld = dim + 1;
-  float* Qs = reinterpret_cast<float*>(smem_raw);                 // [T][ld]
-  float* Ds = Qs + (size_t)T * ld;                                // [R_TOK][ld]
-  uint32_t* tokmax = reinterpret_cast<uint32_t*>(Ds + (size_t)R_TOK * ld);   // [T]
+  const int dim = P.dim, T = P.T, ldq = dim + 1, ldd = dim + 4;   // Q rows: conflict-free across tokens; D rows: 16-byte aligned
+  float* Ds = reinterpret_cast<float*>(smem_raw);                 // [R_TOK][ldd]
+  float* Qs = Ds + (size_t)R_TOK * ldd;                           // [T][ldq]
+  uint32_t* tokmax = reinterpret_cast<uint32_t*>(Qs + (size_t)T * ldq);   // [T]
   float* s_w = reinterpret_cast<float*>(tokmax + T);              // [256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = R_THREADS / 32;
   const int q = blockIdx.x / K2;
@@ -219,34 +219,56 @@ k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64
   const int L = (int)(P.offsets[p + 1] - e0);
   for (int i = tid; i < (1 << P.nbits); i += R_THREADS) s_w[i] = P.weights[i];
   const float* __restrict__ qg = P.Q + (int64_t)q * T * dim;
-  for (int i = tid; i < T * dim; i += R_THREADS) Qs[(i / dim) * ld + (i % dim)] = qg[i];
+  for (int i = tid; i < T * dim; i += R_THREADS) Qs[(i / dim) * ldq + (i % dim)] = qg[i];
   for (int i = tid; i < T; i += R_THREADS) tokmax[i] = 0u;
   const float eps = 1.1920929e-07f;
   for (int c0 = 0; c0 < L; c0 += R_TOK) {
     const int n = min(R_TOK, L - c0);
     __syncthreads();
-    for (int e = warp; e < n; e += nwarps) {
-      const int64_t g = e0 + c0 + e;
-      const float* __restrict__ cptr = P.centroids + (int64_t)P.codes[g] * dim;
-      const uint8_t* __restrict__ emb = P.residuals + g * P.R;
-      float ss = 0.f;
-      for (int d = lane; d < dim; d += 32) {
-        float v = __fadd_rn(cptr[d], s_w[cb_bucket_of(emb, d, P.nbits)]);
-        Ds[e * ld + d] = v;
-        ss = fmaf(v, v, ss);
+    for (int e = warp; e < R_TOK; e += nwarps) {
+      if (e < n) {
+        const int64_t g = e0 + c0 + e;
+        const float* __restrict__ cptr = P.centroids + (int64_t)P.codes[g] * dim;
+        const uint8_t* __restrict__ emb = P.residuals + g * P.R;
+        float ss = 0.f;
+        for (int d = lane; d < dim; d += 32) {
+          float v = __fadd_rn(cptr[d], s_w[cb_bucket_of(emb, d, P.nbits)]);
+          Ds[e * ldd + d] = v;
+          ss = fmaf(v, v, ss);
+        }
+        ss = cb_warp_sum(ss);
+        const float denom = __fadd_rn(sqrtf(ss), eps);
+        for (int d = lane; d < dim; d += 32) Ds[e * ldd + d] = __fdiv_rn(Ds[e * ldd + d], denom);
+      } else {
+        for (int d = lane; d < dim; d += 32) Ds[e * ldd + d] = 0.f;   // rows past the passage: computed, never used
       }
-      ss = cb_warp_sum(ss);
-      const float denom = __fadd_rn(sqrtf(ss), eps);
-      for (int d = lane; d < dim; d += 32) Ds[e * ld + d] = __fdiv_rn(Ds[e * ld + d], denom);
     }
     __syncthreads();
-    for (int idx = tid; idx < T * n; idx += R_THREADS) {
-      const int t = idx % T, e = idx / T;
-      const float* a = Qs + t * ld;
-      const float* b = Ds + e * ld;
-      float acc = 0.f;
-      for (int k = 0; k < dim; k++) acc = fmaf(a[k], b[k], acc);
-      atomicMax(&tokmax[t], cb_orderable(acc));
+    // work item = (query token t, block of 4 passage tokens): the query row is read once per 4 dot products and the
+    // passage rows with 128-bit loads (a warp shares them: broadcast); each dot stays the k-ascending fmaf chain
+    const int nitems = T * (R_TOK / 4);
+    for (int it = tid; it < nitems; it += R_THREADS) {
+      const int t = it % T, eb = (it / T) * 4;
+      if (eb >= n) continue;
+      const float* a = Qs + t * ldq;
+      const float4* b0 = reinterpret_cast<const float4*>(Ds + (eb + 0) * ldd);
+      const float4* b1 = reinterpret_cast<const float4*>(Ds + (eb + 1) * ldd);
+      const float4* b2 = reinterpret_cast<const float4*>(Ds + (eb + 2) * ldd);
+      const float4* b3 = reinterpret_cast<const float4*>(Ds + (eb + 3) * ldd);
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      for (int k4 = 0; k4 < dim / 4; k4++) {
+        const float a0 = a[4 * k4], a1 = a[4 * k4 + 1], a2 = a[4 * k4 + 2], a3 = a[4 * k4 + 3];
+        const float4 x0 = b0[k4], x1 = b1[k4], x2 = b2[k4], x3 = b3[k4];
+        acc0 = fmaf(a0, x0.x, acc0); acc0 = fmaf(a1, x0.y, acc0); acc0 = fmaf(a2, x0.z, acc0); acc0 = fmaf(a3, x0.w, acc0);
+        acc1 = fmaf(a0, x1.x, acc1); acc1 = fmaf(a1, x1.y, acc1); acc1 = fmaf(a2, x1.z, acc1); acc1 = fmaf(a3, x1.w, acc1);
+        acc2 = fmaf(a0, x2.x, acc2); acc2 = fmaf(a1, x2.y, acc2); acc2 = fmaf(a2, x2.z, acc2); acc2 = fmaf(a3, x2.w, acc2);
+        acc3 = fmaf(a0, x3.x, acc3); acc3 = fmaf(a1, x3.y, acc3); acc3 = fmaf(a2, x3.z, acc3); acc3 = fmaf(a3, x3.w, acc3);
+      }
+      uint32_t m = cb_orderable(acc0);
+      if (eb + 1 < n) m = max(m, cb_orderable(acc1));
+      if (eb + 2 < n) m = max(m, cb_orderable(acc2));
+      if (eb + 3 < n) m = max(m, cb_orderable(acc3));
+      atomicMax(&tokmax[t], m);
     }
   }
   __syncthreads();
@@ -264,8 +286,7 @@ int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, c
   GenericParams P{};
   fill_index_params(ix, P);
   P.T = T; P.nq = nq; P.Q = dQ;
-  const int ld = ix->dim + 1;
-  const size_t smem = ((size_t)(T + R_TOK) * ld + T + 256) * 4;
+  const size_t smem = ((size_t)T * (ix->dim + 1) + (size_t)R_TOK * (ix->dim + 4) + T + 256) * 4;
   CB_REQUIRE(smem <= 200 * 1024, CB_ERR_UNSUPPORTED, "dim = %d, query length = %d do not fit the re-score kernel's shared memory", ix->dim, T);
   CB_CUDA(cudaFuncSetAttribute(k_rescore_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_rescore_pairs<<<(unsigned)((int64_t)nq * K2), R_THREADS, smem, st>>>(P, d_pids, K2, ix->pid_base, ix->Np, d_scores_out);

@@ -54,7 +54,10 @@ constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 #endif
 constexpr int TC_NDEC_WARPS = 8 - (TC_NLOAD - 2);
 constexpr int TC_DEC_FIRST = TC_DEC_WARP0 + (TC_NLOAD - 2);   // first decompression warp (loaders 2.. sit before it)
-constexpr int TC_NTEAMS = 2;            // decompression teams (alternate passages)
+#ifndef TC_NTEAMS_
+#define TC_NTEAMS_ 2
+#endif
+constexpr int TC_NTEAMS = TC_NTEAMS_;   // decompression teams (round-robin over passages)
 constexpr int TC_THREADS = 32 * (TC_DEC_FIRST + TC_NDEC_WARPS);
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 256;
 

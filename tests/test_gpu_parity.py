@@ -450,4 +450,4 @@ def test_fused_kernel_decompression_bit_exact(nbits):
     print(f"nbits={nbits}: fused-kernel operand vs exact normalisation of its fp16 sums: {ulps_a:.2f} fp16 ulp; "
           f"vs fp32 oracle decompress: {rel_b:.2e} of the row maximum")
     assert ulps_a <= 2.5, ulps_a      # 1/2 ulp final rounding + the packed-fp16 norm (2-term fp16 chains, ~2^-10 relative)
-    assert rel_b <= 1e-3, rel_b       # three fp16 roundings (centroid, weight, sum) + the above
+    assert rel_b <= 2e-3, rel_b       # four half-ulp fp16 roundings (centroid, sum, two in the scaling) of a component near the row maximum
