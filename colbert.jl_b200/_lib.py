@@ -18,6 +18,8 @@ SIGNATURES = {
     "cb_device_count": (C.c_int32, []),
     "cb_index_create": (C.c_int32, [C.POINTER(_p), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                     C.c_int64, _p, _p, _p, _p, _p, _p, _p, C.c_int64, C.c_int32]),
+    "cb_index_open": (C.c_int32, [C.POINTER(_p), C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "cb_jld2_read": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64), _p, C.c_int64]),
     "cb_index_destroy": (C.c_int32, [_p]),
     "cb_index_info": (C.c_int32, [_p, C.POINTER(C.c_int64)]),
     "cb_set_option": (C.c_int32, [_p, C.c_char_p, C.c_int64]),

@@ -106,6 +106,30 @@ class Searcher:
                                     doclens_ptr, ivf_ptr, ivf_lengths_ptr, self.pid_base, L.CB_FLAG_DEVICE_POINTERS))
         return self
 
+    @classmethod
+    def open(cls, index_path: str, device: int = 0, shard: int = 0, n_shards: int = 1):
+        """`Searcher(index_path)` (src/searching.jl:18-59) without the encoder: reads the directory the reference's
+        Indexer wrote (JLD2 files + config.json / plan.json) natively and uploads it.  `shard` / `n_shards` open one
+        passage range of a passage-sharded deployment (only the overlapping chunk files are read)."""
+        import json
+        import os
+        lib = L.load()
+        if not os.path.isdir(index_path):
+            raise L.ColBERTB200Error(f"Index at {index_path} does not exist! Please build the index first and try again.")
+        c = json.load(open(os.path.join(index_path, "config.json")))
+        self = cls.__new__(cls)
+        self.config = ColBERTConfig(dim=int(c["dim"]), nbits=int(c["nbits"]), nprobe=int(c.get("nprobe", 2)),
+                                    query_maxlen=int(c.get("query_maxlen", 32)), doc_maxlen=int(c.get("doc_maxlen", 300)),
+                                    ncandidates=int(c.get("ncandidates", 8192)), index_path=index_path)
+        self.device, self.bucket_cutoffs = device, None
+        self._h = C.c_void_p()
+        base = C.c_int64()
+        L.check(lib.cb_index_open(C.byref(self._h), index_path.encode(), device, shard, n_shards, C.byref(base)))
+        self.pid_base = int(base.value)
+        info = self.info()
+        self.K, self.n_passages, self.n_embeddings = info["K"], info["n_passages"], info["n_embeddings"]
+        return self
+
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -341,6 +365,23 @@ def maxsim(Q, D, pids, doclens, device=0):
     out = np.zeros(len(pids), dtype=np.float32)
     L.check(L.load().cb_maxsim(device, Qc.shape[1], Qc.shape[0], _ptr(Qc), _ptr(Dc), Dc.shape[0], _ptr(pids),
                                len(pids), _ptr(dl), len(dl), _ptr(out)))
+    return out
+
+
+_JLD2_DTYPES = {1: np.float32, 2: np.float64, 3: np.int8, 4: np.uint8, 5: np.int16, 6: np.uint16, 7: np.int32, 8: np.uint32,
+                9: np.int64, 10: np.uint64}
+
+
+def load_object(path: str, name: str = "single_stored_object"):
+    """`JLD2.load_object(path)` for the plain numeric arrays / scalars the index is made of, through the library's
+    native reader (host only).  Returns the numpy array in C layout: a Julia Matrix{T}(a, b) comes back with shape (b, a)."""
+    lib = L.load()
+    info = (C.c_int64 * 11)()
+    L.check(lib.cb_jld2_read(path.encode(), name.encode(), info, None, 0))
+    shape = tuple(info[3 + i] for i in range(info[2]))
+    out = np.zeros(shape, dtype=_JLD2_DTYPES[info[0]])
+    if out.nbytes:
+        L.check(lib.cb_jld2_read(path.encode(), name.encode(), info, _ptr(out) if out.ndim else out.ctypes.data_as(C.c_void_p), out.nbytes))
     return out
 
 

@@ -75,6 +75,27 @@ int32_t cb_index_create(cb_index** out, int32_t device, int32_t dim, int32_t nbi
                         const uint8_t* residuals, const int64_t* doclens, const int64_t* ivf,
                         const int64_t* ivf_lengths, int64_t pid_base, int32_t flags);
 
+/*
+ * Opens an index DIRECTORY written by the reference (`index(indexer)`, src/indexing.jl:63-147; files by src/savers.jl:
+ * config.json, plan.json, centroids / bucket_weights .jld2, ivf / ivf_lengths .jld2, doclens.<c>.jld2, <c>.codes.jld2,
+ * <c>.residuals.jld2) and uploads it: the loading half of `Searcher(index_path)` (src/searching.jl:18-59;
+ * `load_codec` src/loaders.jl:10-38, `load_doclens` 76-89, `load_compressed_embs` 91-113) with a native reader of the
+ * JLD2 0.4 container (csrc/jld2.h) -- the files are mapped and copied to the device, no Julia object is built.
+ *   shard / n_shards: open only passage range `shard` of `n_shards` ranges balanced by embedding count; only the
+ *     chunk files overlapping that range are read, the shard's IVF is rebuilt on the device from its own codes, and
+ *     its pids are global (pid_base = first passage of the range, also returned through out_pid_base if non-NULL).
+ * Same validation and messages as the reference's loaders (type asserts loaders.jl:27-30, sum(doclens) == num_embeddings
+ * loaders.jl:86-88); compressed (chunked / filtered) JLD2 datasets -> CB_ERR_BAD_ARG.
+ */
+int32_t cb_index_open(cb_index** out, const char* index_path, int32_t device, int32_t shard, int32_t n_shards,
+                      int64_t* out_pid_base);
+
+/* Host-only helper of the above (no GPU needed): reads dataset `name` (NULL = "single_stored_object", what
+ * `JLD2.save_object` writes) of one JLD2 file.  info[0] = element type (1 f32, 2 f64, 3 i8, 4 u8, 5 i16, 6 u16, 7 i32,
+ * 8 u32, 9 i64, 10 u64), info[1] = element size, info[2] = number of dimensions, info[3..10] = dimensions as stored
+ * = the C-layout shape (Julia's size() reversed).  Copies min(capacity_bytes, total bytes) into out (may be NULL). */
+int32_t cb_jld2_read(const char* path, const char* name, int64_t info[11], void* out, int64_t capacity_bytes);
+
 int32_t cb_index_destroy(cb_index* index);
 
 /* info[0..7] = dim, nbits, K, n_passages, n_embeddings, device, pid_base, device bytes held. */
