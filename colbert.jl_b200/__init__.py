@@ -5,8 +5,8 @@ csrc/ (hand-written sm_100a CUDA behind the C ABI of include/colbert_b200.h, bui
 lib/libcolbert_b200.so); this package is the host-side mirror of the reference's interface."""
 from ._lib import (LIB_PATH, SIGNATURES, BoundsError, ColBERTB200Error, CudaError, DimensionMismatch, DomainError,
                    OutOfMemory, Unsupported, load)
-from .searcher import (ColBERTConfig, Searcher, _build_emb2pid, decompress, load_object, maxsim, merge_topk, retrieve, search)
+from .searcher import (ColBERTConfig, MultiSearcher, Searcher, _build_emb2pid, compress, decompress, load_object, maxsim, merge_topk, retrieve, search)
 
-__all__ = ["ColBERTConfig", "Searcher", "search", "retrieve", "decompress", "maxsim", "merge_topk", "load_object",
+__all__ = ["ColBERTConfig", "Searcher", "MultiSearcher", "search", "retrieve", "decompress", "compress", "maxsim", "merge_topk", "load_object",
            "_build_emb2pid", "load", "LIB_PATH", "SIGNATURES", "ColBERTB200Error", "DimensionMismatch",
            "DomainError", "CudaError", "OutOfMemory", "Unsupported", "BoundsError"]

@@ -28,11 +28,17 @@ SIGNATURES = {
     "cb_search_batch_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "cb_probe_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "cb_search_batch_cells_device": (C.c_int32, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
+    "cb_multi_create": (C.c_int32, [C.POINTER(_p), C.c_int32, C.POINTER(_p)]),
+    "cb_multi_open": (C.c_int32, [C.POINTER(_p), C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "cb_multi_destroy": (C.c_int32, [_p]),
+    "cb_multi_info": (C.c_int32, [_p, C.POINTER(C.c_int32), C.POINTER(_p), C.c_int32]),
+    "cb_multi_search_batch": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     "cb_search_batch_plaid": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _p, _p, _p]),
     "cb_search_batch_plaid_device": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "cb_probe": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "cb_retrieve": (C.c_int32, [_p, _p, C.c_int32, C.c_int32, _p, C.c_int64, C.POINTER(C.c_int64)]),
     "cb_decompress": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _p, _p, _p, _p, C.c_int64, _p, _p, _p]),
+    "cb_compress": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _p, _p, _p, C.c_int64, _p, _p]),
     "cb_maxsim": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _p, _p, C.c_int64, _p, C.c_int64, _p, C.c_int64, _p]),
     "cb_score_pids": (C.c_int32, [_p, _p, C.c_int32, _p, C.c_int64, _p]),
     "cb_debug_tc_operand": (C.c_int32, [_p, _p, C.c_int64, _p, _p, C.c_int64]),

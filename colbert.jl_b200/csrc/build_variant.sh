@@ -7,7 +7,7 @@ NAME=$1; EXTRA=${2:-}
 mkdir -p ../lib_ab ../_build_ab/$NAME
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $EXTRA"
-for f in index index_open stage1 stage1_tc stage2 stage34_generic stage34_tc stage5 search hooks plaid; do
+for f in index index_open multi stage1 stage1_tc stage2 stage34_generic stage34_tc stage5 search hooks plaid; do
   $NVCC $FLAGS -c $f.cu -o ../_build_ab/$NAME/$f.o &
 done
 g++ -O2 -std=c++17 -fPIC -c jld2.cpp -o ../_build_ab/$NAME/jld2.o

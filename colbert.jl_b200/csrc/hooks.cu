@@ -151,3 +151,91 @@ extern "C" int32_t cb_maxsim(int32_t device, int32_t dim, int32_t T, const float
   CB_CUDA(cudaMemcpy(out_scores, d_s, b_s, cudaMemcpyDeviceToHost));
   return CB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// cb_compress <-> `compress` (src/indexing/codecs/residual.jl:586-604): the step on the other side of the on-disk
+// format.
+//   codes      `compress_into_codes!` (residual.jl:67-81): argmax over centroids of emb . c == stage 1 of the search
+//              path with nprobe = 1: the tcgen05 GEMM with the fused shortlist epilogue (stage1_tc.cu), decided on
+//              fixed-order fp32 dots, ties -> lower centroid id (Julia's argmax returns the first maximum);
+//   residuals  emb - centroids[:, code] (one fp32 subtraction, exactly the reference's), `_bucket_indices`
+//              (residual.jl:348-351: searchsortedfirst(cutoffs, x) - 1 == number of cutoffs < x), `_binarize`
+//              (197-208) and `_packbits` (400-407): bit b of dimension d is flat bit d * nbits + b, LSB first.
+// One thread per OUTPUT BYTE: it rebuilds the <= 8 bucket indices its bits come from (any nbits in 1..8, dimensions
+// may straddle bytes), so the packed rows leave as coalesced byte stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_compress_residuals(const float* __restrict__ embs, const float* __restrict__ centroids, const int32_t* __restrict__ cells,
+                     const float* __restrict__ cutoffs, int64_t n, int dim, int nbits, int R, uint32_t* __restrict__ out_codes,
+                     uint8_t* __restrict__ out_res) {
+  __shared__ float s_cut[255];
+  const int ncut = (1 << nbits) - 1;
+  for (int i = threadIdx.x; i < ncut; i += blockDim.x) s_cut[i] = cutoffs[i];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * R) return;
+  const int64_t e = i / R;
+  const int j = (int)(i % R);
+  const int32_t code = cells[e];                                  // 0-based centroid id
+  if (j == 0) out_codes[e] = (uint32_t)(code + 1);
+  const float* __restrict__ x = embs + e * dim;
+  const float* __restrict__ c = centroids + (int64_t)code * dim;
+  uint32_t byte = 0;
+  int d_prev = -1;
+  uint32_t bucket = 0;
+  for (int t = 0; t < 8; t++) {
+    const int flat = 8 * j + t, d = flat / nbits, b = flat % nbits;
+    if (d != d_prev) {
+      const float r = __fsub_rn(x[d], c[d]);
+      int lo = 0, hi = ncut;                                      // first index with cutoffs[idx] >= r == count of cutoffs < r
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cut[mid] < r) lo = mid + 1; else hi = mid; }
+      bucket = (uint32_t)lo;
+      d_prev = d;
+    }
+    byte |= ((bucket >> b) & 1u) << t;
+  }
+  out_res[i] = (uint8_t)byte;
+}
+
+extern "C" int32_t cb_compress(int32_t device, int32_t dim, int32_t nbits, int64_t K, const float* centroids, const float* bucket_cutoffs,
+                               const float* embs, int64_t n, uint32_t* out_codes, uint8_t* out_residuals) {
+  CB_REQUIRE(dim > 0 && dim % 8 == 0, CB_ERR_DOMAIN, "dims should be a multiple of 8!");                 // residual.jl:523
+  CB_REQUIRE(nbits >= 1 && nbits <= CB_MAX_NBITS, CB_ERR_UNSUPPORTED, "nbits must be in 1..%d", CB_MAX_NBITS);
+  CB_REQUIRE(K >= 1 && n >= 0, CB_ERR_BAD_ARG, "bad sizes");
+  CB_REQUIRE(centroids && bucket_cutoffs && (n == 0 || (embs && out_codes && out_residuals)), CB_ERR_BAD_ARG, "NULL argument");
+  CB_REQUIRE(cb_device_count() > 0, CB_ERR_CUDA, "no CUDA device is available (no CPU fallback)");
+  if (n == 0) return CB_OK;
+  // a codec-only index handle (no passages) gives stage 1 its centroid images and workspaces
+  cb_index* ix = nullptr;
+  float w0[1 << CB_MAX_NBITS] = {0};
+  CB_TRY(cb_index_create(&ix, device, dim, nbits, K, 0, 0, centroids, w0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));
+  struct GI { cb_index* p; ~GI() { cb_index_destroy(p); } } gi{ix};
+  const int R = dim / 8 * nbits;
+  const int64_t chunk = 1 << 17;                                  // embeddings per pass (bounds the shortlist workspace)
+  const int64_t cmax = n < chunk ? n : chunk;
+  char* base = nullptr;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_e = al(sizeof(float) * (size_t)cmax * dim), b_c = al(sizeof(int32_t) * (size_t)cmax), b_s = al(sizeof(float) * (size_t)cmax),
+               b_oc = al(sizeof(uint32_t) * (size_t)cmax), b_or = al((size_t)cmax * R), b_cut = al(sizeof(float) * 256);
+  CB_CUDA(cudaMalloc((void**)&base, b_e + b_c + b_s + b_oc + b_or + b_cut));
+  struct G { void* p; ~G() { cudaFree(p); } } g{base};
+  float* d_e = (float*)base;
+  int32_t* d_cells = (int32_t*)(base + b_e);
+  float* d_sc = (float*)(base + b_e + b_c);
+  uint32_t* d_oc = (uint32_t*)(base + b_e + b_c + b_s);
+  uint8_t* d_or = (uint8_t*)(base + b_e + b_c + b_s + b_oc);
+  float* d_cut = (float*)(base + b_e + b_c + b_s + b_oc + b_or);
+  CB_CUDA(cudaMemcpy(d_cut, bucket_cutoffs, sizeof(float) * ((1u << nbits) - 1), cudaMemcpyHostToDevice));
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t m = n - o < chunk ? n - o : chunk;
+    CB_CUDA(cudaMemcpy(d_e, embs + o * dim, sizeof(float) * (size_t)m * dim, cudaMemcpyHostToDevice));
+    ix->q_prep_src = nullptr;
+    CB_TRY(cb_stage1_probe(ix, d_e, m, 1, d_cells, d_sc, nullptr));
+    const int64_t nb = m * R;
+    k_compress_residuals<<<(unsigned)((nb + 255) / 256), 256>>>(d_e, ix->centroids, d_cells, d_cut, m, dim, nbits, R, d_oc, d_or);
+    CB_LAUNCH_CHECK();
+    CB_CUDA(cudaMemcpy(out_codes + o, d_oc, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(out_residuals + o * R, d_or, (size_t)m * R, cudaMemcpyDeviceToHost));
+  }
+  return CB_OK;
+}

@@ -65,11 +65,24 @@ k_stage2_mark(const int32_t* __restrict__ cells, int slots, const int64_t* __res
 
 // bitmapT uint32[nq][NpW] (bit p & 31 of word [q][p >> 5]) -> bitmap uint32[Np][W] (bit q & 31 of word
 // [p][q >> 5]).  One CTA per 256 passages, one warp per 32 queries: lane = query reads 8 consecutive
-// words of its row (one full 32-byte sector), 256 ballots transpose them, the CTA's 256 x W output
-// words are staged in shared memory and leave as whole lines.
+// words of its row (one full 32-byte sector); each 32 x 32 bit block (32 queries x 32 passages) is
+// transposed in registers by the five-step butterfly (exchange 16 x 16, 8 x 8, ... 1 x 1 sub-blocks with
+// lane ^ 16, ^ 8, ... -- 5 shuffles per block where the ballot formulation needed 32 ballots and 32
+// single-lane stores); the CTA's 256 x W output words are staged in shared memory (row stride 33: both
+// the per-lane writes and the row-wise read-out are bank-conflict free) and leave as whole lines.
+__device__ __forceinline__ uint32_t transpose32_across_warp(uint32_t x, int lane) {
+  uint32_t y;
+  y = __shfl_xor_sync(0xffffffffu, x, 16); x = (lane & 16) ? ((x & 0xffff0000u) | (y >> 16)) : ((x & 0x0000ffffu) | (y << 16));
+  y = __shfl_xor_sync(0xffffffffu, x, 8);  x = (lane & 8) ? ((x & 0xff00ff00u) | ((y >> 8) & 0x00ff00ffu)) : ((x & 0x00ff00ffu) | ((y & 0x00ff00ffu) << 8));
+  y = __shfl_xor_sync(0xffffffffu, x, 4);  x = (lane & 4) ? ((x & 0xf0f0f0f0u) | ((y >> 4) & 0x0f0f0f0fu)) : ((x & 0x0f0f0f0fu) | ((y & 0x0f0f0f0fu) << 4));
+  y = __shfl_xor_sync(0xffffffffu, x, 2);  x = (lane & 2) ? ((x & 0xccccccccu) | ((y >> 2) & 0x33333333u)) : ((x & 0x33333333u) | ((y & 0x33333333u) << 2));
+  y = __shfl_xor_sync(0xffffffffu, x, 1);  x = (lane & 1) ? ((x & 0xaaaaaaaau) | ((y >> 1) & 0x55555555u)) : ((x & 0x55555555u) | ((y & 0x55555555u) << 1));
+  return x;   // lane p now holds: bit q = bit p of lane q's input
+}
+
 __global__ void __launch_bounds__(1024)
 k_bitmap_transpose(const uint32_t* __restrict__ bitmapT, int nq, int64_t NpW, int64_t Np, int W, uint32_t* __restrict__ bitmap) {
-  __shared__ uint32_t s_out[256 * 32];
+  __shared__ uint32_t s_out[256 * 33];
   const int qw = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t w0 = (int64_t)blockIdx.x * 8;            // first of this CTA's 8 words per query row
   const int q = qw * 32 + lane;
@@ -81,19 +94,15 @@ k_bitmap_transpose(const uint32_t* __restrict__ bitmapT, int nq, int64_t NpW, in
     const uint4 a = src[0], b = src[1];
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
   }
+  if (qw < W) {                                           // (warps beyond the chunk's query words hold only zeros)
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const uint32_t word = __ballot_sync(0xffffffffu, (x[k] >> j) & 1u);
-      if (lane == j) s_out[(k * 32 + j) * 32 + qw] = word;
-    }
+    for (int k = 0; k < 8; k++) s_out[(k * 32 + lane) * 33 + qw] = transpose32_across_warp(x[k], lane);
   }
   __syncthreads();
   const int64_t p0 = (int64_t)blockIdx.x * 256;
   for (int i = threadIdx.x; i < 256 * W; i += 1024) {
     const int pl = i / W, w = i % W;
-    if (p0 + pl < Np) bitmap[(p0 + pl) * W + w] = s_out[pl * 32 + w];
+    if (p0 + pl < Np) bitmap[(p0 + pl) * W + w] = s_out[pl * 33 + w];
   }
 }
 

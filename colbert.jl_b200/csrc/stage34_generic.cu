@@ -202,7 +202,8 @@ int32_t cb_generic_score_list(cb_index* ix, const float* dQ, int nq, int T, cons
 constexpr int R_THREADS = 128, R_TOK = 16;
 
 __global__ void __launch_bounds__(R_THREADS)
-k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64_t pid_base, int64_t Np, float* __restrict__ scores_out) {
+k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, const float* __restrict__ approx, int K2, int k, float band,
+                int64_t pid_base, int64_t Np, float* __restrict__ scores_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int dim = P.dim, T = P.T, ldq = dim + 1, ldd = dim + 4;   // Q rows: conflict-free across tokens; D rows: 16-byte aligned
   float* Ds = reinterpret_cast<float*>(smem_raw);                 // [R_TOK][ldd]
@@ -210,9 +211,15 @@ k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64
   uint32_t* tokmax = reinterpret_cast<uint32_t*>(Qs + (size_t)T * ldq);   // [T]
   float* s_w = reinterpret_cast<float*>(tokmax + T);              // [256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = R_THREADS / 32;
-  const int q = blockIdx.x / K2;
+  const int q = blockIdx.x / K2, j = blockIdx.x % K2;
   const int64_t pid = pids[blockIdx.x];
   if (pid <= 0) { if (tid == 0) scores_out[blockIdx.x] = -INFINITY; return; }
+  if (approx != nullptr && j >= k) {
+    // Candidate j (rank j by tensor-core score) can only enter the exact top-k if its tensor-core score lies within
+    // twice the error bound of the k-th one: k candidates have an exact score >= tau - eps, and exact_j <= approx_j + eps.
+    const float tau = approx[(int64_t)q * K2 + (k - 1)];
+    if (approx[blockIdx.x] < tau - band * fabsf(tau)) { if (tid == 0) scores_out[blockIdx.x] = -INFINITY; return; }
+  }
   const int64_t p = pid - 1 - pid_base;
   if (p < 0 || p >= Np) { if (tid == 0) scores_out[blockIdx.x] = -INFINITY; return; }
   const int64_t e0 = P.offsets[p];
@@ -280,8 +287,8 @@ k_rescore_pairs(GenericParams P, const int64_t* __restrict__ pids, int K2, int64
   }
 }
 
-int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, int K2, float* d_scores_out,
-                                 cudaStream_t st) {
+int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, const float* d_approx, int K2, int k,
+                                 float band, float* d_scores_out, cudaStream_t st) {
   if (nq == 0 || K2 == 0) return CB_OK;
   GenericParams P{};
   fill_index_params(ix, P);
@@ -289,7 +296,7 @@ int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, c
   const size_t smem = ((size_t)T * (ix->dim + 1) + (size_t)R_TOK * (ix->dim + 4) + T + 256) * 4;
   CB_REQUIRE(smem <= 200 * 1024, CB_ERR_UNSUPPORTED, "dim = %d, query length = %d do not fit the re-score kernel's shared memory", ix->dim, T);
   CB_CUDA(cudaFuncSetAttribute(k_rescore_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_rescore_pairs<<<(unsigned)((int64_t)nq * K2), R_THREADS, smem, st>>>(P, d_pids, K2, ix->pid_base, ix->Np, d_scores_out);
+  k_rescore_pairs<<<(unsigned)((int64_t)nq * K2), R_THREADS, smem, st>>>(P, d_pids, d_approx, K2, k, band, ix->pid_base, ix->Np, d_scores_out);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

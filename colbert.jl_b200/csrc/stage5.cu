@@ -212,26 +212,30 @@ extern "C" int32_t cb_merge_topk(int32_t device, int32_t n_lists, int32_t nq, in
 
 // ---------------------------------------------------------------------------------------------
 // final ranking on exact fp32 scores.  The tcgen05 scoring kernel's scores carry ~1e-4 relative error
-// (fp16 operands), enough to reorder near-equal passages and to move the k-th boundary against the
-// reference's fp32 `sortperm(scores, rev = true)[1:k]` (src/searching.jl:125-127).  So stage 5 selects the
-// best K2 = max(2k, k + 16) candidates by tensor-core score, those few pairs are re-scored in exact fp32
-// (k_rescore_pairs = the arithmetic of cb_score_pids) and the final (score desc, pid asc) order -- the
-// reference's stable sort over ascending pids -- is decided on the exact scores.  A query whose K2-th
-// tensor-core score is within the error band of its k-th exact score could in principle have lost a
-// member of its top-k to the cut: such queries are counted (stat "rescore_unsafe"; 0 in every run so far).
+// (fp16 operands; bound used below: eps = 2e-4 |score|), enough to reorder near-equal passages and to move
+// the k-th boundary against the reference's fp32 `sortperm(scores, rev = true)[1:k]`
+// (src/searching.jl:125-127).  So stage 5 selects a pool of the best K2 = max(2k, k + 16) candidates by
+// tensor-core score; of those, the top k and every further one whose tensor-core score lies within 2 eps of
+// the k-th (the only ones that can still enter the exact top-k) are re-scored in exact fp32
+// (k_rescore_pairs = the arithmetic of cb_score_pids), and the final (score desc, pid asc) order -- the
+// reference's stable sort over ascending pids -- is decided on the exact scores.  If even the LAST member of
+// the pool lies inside that band the pool may have been too small: such queries are counted (stat
+// "rescore_unsafe"; 0 in every run so far).
 // ---------------------------------------------------------------------------------------------
-int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, int K2, float* d_scores_out,
-                                 cudaStream_t st);   // stage34_generic.cu
+int32_t cb_generic_rescore_pairs(cb_index* ix, const float* dQ, int nq, int T, const int64_t* d_pids, const float* d_approx, int K2, int k,
+                                 float band, float* d_scores_out, cudaStream_t st);   // stage34_generic.cu
 
-__global__ void k_rescore_guard(const float* __restrict__ approx, const float* __restrict__ exact_sorted, const int64_t* __restrict__ list_off,
-                                const int32_t* __restrict__ lens, int nq, int K2, int k, unsigned long long* __restrict__ stat_unsafe) {
+constexpr float CB_RESCORE_BAND = 4e-4f;   // 2 eps, eps = 2e-4 relative (measured tensor-core score error: <= 1.0e-4)
+
+__global__ void k_rescore_guard(const float* __restrict__ approx, const int64_t* __restrict__ list_off, const int32_t* __restrict__ lens,
+                                int nq, int K2, int k, float band, unsigned long long* __restrict__ stat_unsafe) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   const int64_t n = lens ? (int64_t)lens[q] : list_off[q + 1] - list_off[q];
   if (n <= K2) return;                                   // nothing was cut
-  const float kth = exact_sorted[(int64_t)q * k + (k - 1)];
+  const float tau = approx[(int64_t)q * K2 + (k - 1)];
   const float cut = approx[(int64_t)q * K2 + (K2 - 1)];   // every cut candidate has a tensor-core score <= this
-  if (!(kth - cut > 2.5e-4f * fabsf(kth))) atomicAdd(stat_unsafe, 1ULL);
+  if (!(cut < tau - band * fabsf(tau))) atomicAdd(stat_unsafe, 1ULL);
 }
 
 int32_t cb_final_topk(cb_index* ix, const float* dQ, int nq, int T, int k, const uint64_t* d_pairs, const int64_t* d_list_off,
@@ -254,12 +258,12 @@ int32_t cb_final_topk(cb_index* ix, const float* dQ, int nq, int T, int k, const
   const int kp = pow2_at_least(K2);
   k_topk_select<<<nq, S5_THREADS, sizeof(uint64_t) * kp, st>>>(d_pairs, d_list_off, d_lens, K2, kp, ix->pid_base, f_pids, f_approx);
   CB_LAUNCH_CHECK();
-  CB_TRY(cb_generic_rescore_pairs(ix, dQ, nq, T, f_pids, K2, f_exact, st));
+  CB_TRY(cb_generic_rescore_pairs(ix, dQ, nq, T, f_pids, f_approx, K2, k, CB_RESCORE_BAND, f_exact, st));
   const size_t smem = sizeof(uint64_t) * kp * 2;
   CB_CUDA(cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_merge_topk<<<nq, 256, smem, st>>>(1, nq, K2, k, kp, f_pids, f_exact, d_out_pids, d_out_scores);
   CB_LAUNCH_CHECK();
-  k_rescore_guard<<<(nq + 255) / 256, 256, 0, st>>>(f_approx, d_out_scores, d_list_off, d_lens, nq, K2, k, cb_stats_dev(ix) + 5);
+  k_rescore_guard<<<(nq + 255) / 256, 256, 0, st>>>(f_approx, d_list_off, d_lens, nq, K2, k, CB_RESCORE_BAND, cb_stats_dev(ix) + 5);
   CB_LAUNCH_CHECK();
   return CB_OK;
 }

@@ -271,6 +271,71 @@ class Searcher:
         return norm, raw
 
 
+class MultiSearcher:
+    """The passage-range shards of one index on several GPUs of one box, driven by ONE host thread through
+    cb_multi_* (no torch.distributed, no process per GPU): what a single-process caller such as the reference's
+    `search(searcher, query, k)` needs.  `searchers` = Searcher objects (one per shard, each with its pid_base, on
+    its device); or use `MultiSearcher.open(index_path, n_gpus)` for an index directory."""
+
+    def __init__(self, searchers):
+        lib = L.load()
+        self.searchers = list(searchers)
+        self.config = self.searchers[0].config
+        arr = (C.c_void_p * len(self.searchers))(*[s._h for s in self.searchers])
+        self._m = C.c_void_p()
+        L.check(lib.cb_multi_create(C.byref(self._m), len(self.searchers), arr))
+
+    @classmethod
+    def open(cls, index_path: str, n_gpus: int, device_ids=None):
+        import json
+        import os
+        lib = L.load()
+        self = cls.__new__(cls)
+        c = json.load(open(os.path.join(index_path, "config.json")))
+        self.config = ColBERTConfig(dim=int(c["dim"]), nbits=int(c["nbits"]), nprobe=int(c.get("nprobe", 2)),
+                                    query_maxlen=int(c.get("query_maxlen", 32)), index_path=index_path)
+        self.searchers = []
+        ids = None if device_ids is None else (C.c_int32 * n_gpus)(*device_ids)
+        self._m = C.c_void_p()
+        L.check(lib.cb_multi_open(C.byref(self._m), index_path.encode(), n_gpus, ids))
+        return self
+
+    def search_batch(self, Q, k: int, nprobe: int | None = None):
+        """Q (dim, T, nq) -> (pids (nq, k), scores (nq, k), counts (nq,)) over the whole index."""
+        Q = np.asarray(Q)
+        if Q.ndim == 2:
+            Q = Q[:, :, None]
+        Qc = _c(np.transpose(Q, (2, 1, 0)), np.float32)
+        nq, T, _ = Qc.shape
+        nprobe = self.config.nprobe if nprobe is None else nprobe
+        pids = np.zeros((nq, k), dtype=np.int64)
+        scores = np.full((nq, k), -np.inf, dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.int32)
+        L.check(L.load().cb_multi_search_batch(self._m, _ptr(Qc), nq, T, nprobe, k, _ptr(pids), _ptr(scores), _ptr(counts)))
+        return pids, scores, counts
+
+    def search_batch_ptr(self, q_host_ptr, nq, T, k, pids_ptr, scores_ptr, counts_ptr, nprobe=None):
+        nprobe = self.config.nprobe if nprobe is None else nprobe
+        L.check(L.load().cb_multi_search_batch(self._m, q_host_ptr, nq, T, nprobe, k, pids_ptr, scores_ptr, counts_ptr))
+
+    def close(self):
+        m, self._m = getattr(self, "_m", None), None
+        if m:
+            L.load().cb_multi_destroy(m)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def search(searcher: Searcher, Q, k: int):
     """`search(searcher, query, k)` (src/searching.jl:93-128) minus `encode_queries`: Q is the
     encoder's output for the query, (dim, query_maxlen) -- or (dim, query_maxlen, 1).
@@ -352,6 +417,25 @@ def decompress(dim, nbits, centroids, bucket_weights, codes, residuals, bsize=10
     if return_unnormalized:
         ret.append(raw.T)
     return ret[0] if len(ret) == 1 else tuple(ret)
+
+
+def compress(centroids, bucket_cutoffs, dim, nbits, embs, bsize=10000, device=0):
+    """`compress` (src/indexing/codecs/residual.jl:586-604): centroids (dim, K), embs (dim, n) ->
+    (codes UInt32 (n,) 1-based, residuals UInt8 (dim/8*nbits, n)).  `bsize` accepted for signature compatibility."""
+    if dim % 8 != 0:
+        raise DomainError("dims should be a multiple of 8!")
+    cut = _c(bucket_cutoffs, np.float32)
+    if len(cut) != (1 << nbits) - 1:
+        raise DomainError("length(bucket_cutoffs) should be 2^nbits - 1!")
+    cen = _julia_to_c(centroids, np.float32)
+    e = _julia_to_c(embs, np.float32)
+    if cen.shape[1] != dim or (e.size and e.shape[1] != dim):
+        raise DimensionMismatch("centroids / embs must have `dim` rows")
+    n = e.shape[0]
+    codes = np.zeros(n, dtype=np.uint32)
+    res = np.zeros((n, dim // 8 * nbits), dtype=np.uint8)
+    L.check(L.load().cb_compress(device, dim, nbits, cen.shape[0], _ptr(cen), _ptr(cut), _ptr(e), n, _ptr(codes), _ptr(res)))
+    return codes, res.T
 
 
 def maxsim(Q, D, pids, doclens, device=0):

@@ -46,6 +46,7 @@ extern "C" {
 #define CB_FLAG_DEVICE_POINTERS 1 /* all array arguments are device pointers on `device` */
 
 typedef struct cb_index cb_index; /* opaque: one index shard resident in the HBM of one GPU */
+typedef struct cb_multi cb_multi; /* opaque: the passage-range shards of one index on several GPUs of one box */
 
 /* Library version string, e.g. "colbert_b200 0.1 (sm_100a)". */
 const char* cb_version(void);
@@ -165,6 +166,25 @@ int32_t cb_search_batch_cells_device(cb_index* index, const float* dQ, const int
                                      int32_t T, int32_t nprobe, int32_t k, int64_t* d_out_pids,
                                      float* d_out_scores, int32_t* d_out_counts, void* stream);
 
+/* ---- several GPUs, one process, one host thread (SURVEY 8b "Threading"; the reference is single-process:
+ * src/infra/config.jl:57-58 carries rank / nranks but `search` never uses them) ----
+ * cb_multi_create groups shard handles (passage-range shards of ONE index, each created with its pid_base on its
+ * own device -- cb_index_create, or cb_index_open(path, device, r, n)); the group borrows them.  cb_multi_open opens
+ * the n shards of an index directory itself (device_ids NULL = devices 0..n-1) and owns them.  Two shards may share
+ * a device (useful for tests). */
+int32_t cb_multi_create(cb_multi** out, int32_t n_shards, cb_index* const* shards);
+int32_t cb_multi_open(cb_multi** out, const char* index_path, int32_t n_gpus, const int32_t* device_ids);
+int32_t cb_multi_destroy(cb_multi* multi);
+/* *n_shards = number of shards; the first min(capacity, n) handles are written to shards (may be NULL). */
+int32_t cb_multi_info(const cb_multi* multi, int32_t* n_shards, cb_index** shards, int32_t capacity);
+
+/* `search` minus the encoder over the whole sharded index (src/searching.jl:103-127), host buffers as cb_search_batch:
+ * Q is uploaded once and forwarded to the peers over NVLink, stage 1 is split by query across the devices, every
+ * device scores its own passage range, the per-shard top-k lists are merged on the first device by (score desc, pid
+ * asc).  Results are bit-identical to cb_search_batch on the unsharded index.  out_counts[q] = candidates over all shards. */
+int32_t cb_multi_search_batch(cb_multi* multi, const float* Q, int32_t nq, int32_t T, int32_t nprobe, int32_t k,
+                              int64_t* out_pids, float* out_scores, int32_t* out_counts);
+
 /* PLAID-style pruned search (BASELINE.json config 5).  NOT a reference function: ColBERT.jl lists PLAID
  * pruning as roadmap (README.md:187); the semantics are defined by oracle/oracle.py `plaid_search`
  * on top of the reference's own `retrieve` / `decompress` / `maxsim`:
@@ -207,6 +227,17 @@ int32_t cb_decompress(int32_t device, int32_t dim, int32_t nbits, int64_t K,
                       const float* centroids, const float* bucket_weights,
                       const uint32_t* codes, const uint8_t* residuals, int64_t n,
                       float* out_embs, uint8_t* out_bucket_idx, float* out_unnormalized);
+
+/* The writer side of the codec: `compress(centroids, bucket_cutoffs, dim, nbits, embs)` (src/indexing/codecs/residual.jl:586-604)
+ * = `compress_into_codes!` (67-81: argmax over centroids of emb . c, first maximum wins) + `binarize` (518-536:
+ * `_bucket_indices` 348-351, `_binarize` 197-208, `_packbits` 400-407) of emb - centroids[:, code].
+ *   centroids float[K][dim], bucket_cutoffs float[2^nbits - 1] (ascending), embs float[n][dim]
+ *   out_codes uint32[n] 1-based, out_residuals uint8[n][dim/8*nbits]
+ * The codes come from the stage-1 tensor-core GEMM with nprobe = 1 and are decided on fixed-order fp32 dot products;
+ * given the codes the packed bytes are bit-exact (`decompress_residuals(binarize(x))` inverts, residual.jl test 975-991). */
+int32_t cb_compress(int32_t device, int32_t dim, int32_t nbits, int64_t K, const float* centroids,
+                    const float* bucket_cutoffs, const float* embs, int64_t n, uint32_t* out_codes,
+                    uint8_t* out_residuals);
 
 /* Stage 4 alone: `maxsim(Q, D, pids, doclens)` (src/search/ranking.jl:69-86) in fp32.
  *   Q float[T][dim], D float[M][dim], pids int64[n_pids] 1-based, doclens int64[n_doclens].

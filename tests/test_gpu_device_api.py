@@ -163,3 +163,57 @@ def test_out_of_range_queries_are_routed_to_the_fp32_kernel(small):
             np.testing.assert_allclose(sc[q], osc, rtol=1e-4)
         _device_search(s, Q[:6], 10)                           # and the gate re-opens for the next batch
         assert s.stat("tc_pairs") > 0
+
+
+# --------------------------------------------------------------------------------------------
+# several shards behind the C ABI, one process, one host thread (cb_multi_*)
+# --------------------------------------------------------------------------------------------
+def _multi_equals_unsharded(ix, Q, devices):
+    from colbert_jl_b200 import sharding as SH
+    Qj = np.transpose(Q, (2, 1, 0))
+    with _searcher(ix) as whole:
+        ref = whole.search_batch(Qj, 10)
+    n = len(devices)
+    shards = []
+    for r, (lo, hi, e_lo, e_hi) in enumerate(SH.shard_slices(ix["doclens"], n)):
+        part = S.take_shard(ix, lo, hi)
+        cfg = cb.ColBERTConfig(dim=128, nbits=ix["nbits"], nprobe=2, query_maxlen=32)
+        shards.append(cb.Searcher(cfg, part["centroids"].T, None, part["bucket_weights"], None, None, part["doclens"], part["codes"],
+                                  part["residuals"].T, device=devices[r], pid_base=lo))
+    try:
+        with cb.MultiSearcher(shards) as m:
+            for _ in range(2):                                  # twice: workspaces are reused across batches
+                got = m.search_batch(Qj, 10)
+                for a, b in zip(ref, got):
+                    assert np.array_equal(a, b)
+            got5 = m.search_batch(Qj[:, :, :5], 10)             # nq not a multiple of the shard count
+            assert np.array_equal(got5[0], ref[0][:5]) and np.array_equal(got5[1], ref[1][:5])
+    finally:
+        for s in shards:
+            s.close()
+
+
+def test_multi_three_shards_on_one_device_equal_unsharded(small):
+    ix, Q = small
+    _multi_equals_unsharded(ix, Q, [0, 0, 0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_multi_two_gpus_equal_unsharded(small):
+    ix, Q = small
+    _multi_equals_unsharded(ix, Q, [0, 1])
+
+
+def test_multi_open_index_directory(small, tmp_path):
+    from tests import jld2_writer as W
+    ix, Q = small
+    path = str(tmp_path / "ix")
+    W.write_index(path, ix, n_chunks=5)
+    Qj = np.transpose(Q, (2, 1, 0))
+    with _searcher(ix) as whole:
+        ref = whole.search_batch(Qj, 10)
+    ndev = min(2, torch.cuda.device_count())
+    with cb.MultiSearcher.open(path, 2, device_ids=[0, ndev - 1]) as m:
+        got = m.search_batch(Qj, 10)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)

@@ -451,3 +451,51 @@ def test_fused_kernel_decompression_bit_exact(nbits):
           f"vs fp32 oracle decompress: {rel_b:.2e} of the row maximum")
     assert ulps_a <= 2.5, ulps_a      # 1/2 ulp final rounding + the packed-fp16 norm (2-term fp16 chains, ~2^-10 relative)
     assert rel_b <= 2e-3, rel_b       # four half-ulp fp16 roundings (centroid, sum, two in the scaling) of a component near the row maximum
+
+
+# --------------------------------------------------------------------------------------------
+# f4: cb_compress <-> `compress` (src/indexing/codecs/residual.jl:586-604)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbits", [1, 2, 3, 4, 8])
+def test_compress_vs_oracle(nbits):
+    """codes == the oracle's argmax (fixture embeddings have a top-1 rank gap far above fp32 rounding, like the
+    queries of the search fixtures); packed residual bytes bit-exact, dimensions straddling bytes included."""
+    dim, K, n = 128, 700, 3000            # K not a multiple of the 128-centroid tile
+    cen = O._normalize_array(rng.standard_normal((dim, K)).astype(np.float32))                    # (dim, K)
+    embs = S.make_queries(cen.T.copy(), n // 32 + 1, seed=900 + nbits, nprobe=1).reshape(-1, dim)[:n].T.copy()   # (dim, n)
+    cut = np.sort(rng.normal(0, 0.03, (1 << nbits) - 1).astype(np.float32))
+    codes, res = cb.compress(cen, cut, dim, nbits, embs)
+    o_codes, o_res = O.compress(cen, cut, dim, nbits, embs)
+    assert codes.dtype == np.uint32 and res.dtype == np.uint8 and res.shape == (dim // 8 * nbits, n)
+    assert np.array_equal(codes, o_codes)
+    assert np.array_equal(res, o_res)
+
+
+def test_compress_inverts_through_decompress_residuals():   # test/indexing/codecs/residual.jl:975-991
+    """decompress_residuals(binarize(x)) == bucket_weights[searchsortedfirst(cutoffs, x)]: with one zero centroid the
+    residual IS the embedding and cb_decompress's un-normalised output IS bucket_weights[idx]."""
+    for nbits in (1, 2, 5):
+        dim = 8 * int(rng.integers(1, 21))
+        cut = np.sort(rng.random((1 << nbits) - 1, dtype=np.float32))
+        w = np.sort(rng.random(1 << nbits, dtype=np.float32))
+        x = rng.random((dim, int(rng.integers(1, 100))), dtype=np.float32)
+        zero = np.zeros((dim, 1), np.float32)
+        codes, packed = cb.compress(zero, cut, dim, nbits, x)
+        assert np.all(codes == 1)
+        assert np.array_equal(packed, O.binarize(dim, nbits, cut, x))
+        _, raw = cb.decompress(dim, nbits, zero, w, codes, packed, return_unnormalized=True)
+        assert np.array_equal(raw, w[np.searchsorted(cut, x, side="left")])
+
+
+def test_compress_ties_and_errors():
+    dim = 16
+    cen = np.zeros((dim, 5), np.float32)
+    cen[0, 1] = cen[0, 3] = 1.0                       # centroids 2 and 4 identical: argmax returns the first maximum
+    x = np.zeros((dim, 2), np.float32)
+    x[0, :] = 1.0
+    codes, _ = cb.compress(cen, np.zeros(3, np.float32), dim, 2, x)
+    assert codes.tolist() == [2, 2]
+    with pytest.raises(cb.DomainError):               # residual.jl:525
+        cb.compress(cen, np.zeros(2, np.float32), dim, 2, x)
+    with pytest.raises(cb.DomainError):               # residual.jl:523
+        cb.compress(np.zeros((12, 5), np.float32), np.zeros(3, np.float32), 12, 2, np.zeros((12, 2), np.float32))
