@@ -49,6 +49,9 @@ constexpr int TC_MAX_ASTAGES = 6;
 constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots == tile barriers)
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
 constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
+#ifndef TC_ABLATE
+#define TC_ABLATE 0                    // measurement-only builds (results are garbage): 1 = one 8 KB query copy per group instead of
+#endif                                 // four, 2 = epilogue reads 16 accumulator columns, 4 = no decompression, 8 = 2 of 8 MMA K-steps
 #ifndef TC_NLOAD
 #define TC_NLOAD 2                     // query-tile loader warps (2: warps 2-3; 4: two more taken from the decompression pool)
 #endif
@@ -350,7 +353,7 @@ k_maxsim_tc(TcParams P) {
         const uint32_t st_g = st, par_g = a_par;
         if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
         ptx::mbar_wait(&bar->a_empty[st_g], par_g, 9);
-        const int nqg = min(4, ncand - g * 4);
+        const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
         uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
         const int nmine = (nqg - li + TC_NLOAD - 1) / TC_NLOAD;      // queries li, li + TC_NLOAD, ... < nqg
         if (nmine <= 0) {
@@ -504,7 +507,7 @@ k_maxsim_tc(TcParams P) {
             const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
             const uint32_t b_lo = c ? b_lo1 : b_lo0, kb = c ? kb1 : kb0, idesc = c ? idesc1 : idesc0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
               const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
               const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
               ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
@@ -568,7 +571,7 @@ k_maxsim_tc(TcParams P) {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 chains: ILP for the ALU pipe
         for (int c = 0; c < nchunk; c++, ud++) {
           const int ds = ud & 1;
-          const int ncol = c ? n1 : n0;
+          const int ncol = (TC_ABLATE & 2) ? 16 : (c ? n1 : n0);
           const int nfull = ncol >> 5;           // full 32-column chunks (<= 7)
           ptx::mbar_wait(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11);
           fpar ^= 1u << ds;
@@ -662,7 +665,7 @@ k_maxsim_tc(TcParams P) {
       if (stop) break;
       const int slot = e & (TC_NSLOT - 1);
       const Meta& m = meta[slot];
-      tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
+      if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
