@@ -41,10 +41,13 @@ namespace {
 #ifndef TC_EPI_SETS
 #define TC_EPI_SETS 1                  // epilogue warp sets (each set = 4 warps = one accumulator consumer)
 #endif
+#ifndef TC_TMEM_A
+#define TC_TMEM_A 0                    // 1 = the A operand (query tiles) is forwarded shared memory -> registers -> TENSOR MEMORY by
+#endif                                 // four converter warps and tcgen05.mma reads it from there (see "what bounds it" above); 0 = A from shared memory
 constexpr int TC_NEPI_WARPS = 4 * TC_EPI_SETS;
 constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first decompression warp
 constexpr int TC_DIM = 128, TC_T = 32;
-constexpr int TC_MAX_BROWS = 240;      // rows (tokens) per chunk; multiple of 16, <= 256 TMEM columns
+constexpr int TC_MAX_BROWS = TC_TMEM_A ? 192 : 240;   // rows (tokens) per chunk; multiple of 16, <= TC_D_COLS TMEM columns
 constexpr int TC_MAX_ASTAGES = 6;
 constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots == tile barriers)
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
@@ -61,8 +64,12 @@ constexpr int TC_DEC_FIRST = TC_DEC_WARP0 + (TC_NLOAD - 2);   // first decompres
 #define TC_NTEAMS_ 2
 #endif
 constexpr int TC_NTEAMS = TC_NTEAMS_;   // decompression teams (round-robin over passages)
-constexpr int TC_THREADS = 32 * (TC_DEC_FIRST + TC_NDEC_WARPS);
-constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 256;
+constexpr int TC_CONV_WARP0 = TC_DEC_FIRST + TC_NDEC_WARPS;   // converter warps (TC_TMEM_A): one per TMEM lane quarter
+constexpr int TC_THREADS = 32 * (TC_CONV_WARP0 + (TC_TMEM_A ? 4 : 0));
+// tensor memory: two accumulators of TC_D_COLS fp32 columns; with TC_TMEM_A also TC_NTA query-tile stages of 64 columns
+// (128 lanes x 128 fp16 = 64 packed 32-bit columns: lane = (query, token) row, column j = dims 2j, 2j+1)
+constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = TC_TMEM_A ? 192 : 256, TC_A_COL0 = 2 * TC_D_COLS, TC_A_TCOLS = 64;
+constexpr int TC_NTA = 2;
 
 struct Meta {            // one passage entry, written by the scheduler
   int ncand;             // candidate queries of the passage (< 0: end of stream)
@@ -80,6 +87,7 @@ struct Barriers {
   uint64_t b_full[TC_NSLOT], b_empty[TC_NSLOT], meta_full[TC_NSLOT], meta_empty[TC_NSLOT];
   uint64_t a_full[TC_MAX_ASTAGES], a_empty[TC_MAX_ASTAGES];
   uint64_t d_full[TC_EPI_SETS][2], d_empty[2];
+  uint64_t at_full[TC_NTA], at_empty[TC_NTA];   // query-tile stages in tensor memory (TC_TMEM_A)
 };
 
 struct TcParams {
@@ -319,13 +327,14 @@ k_maxsim_tc(TcParams P) {
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
       ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], 1);
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS);
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + (TC_TMEM_A ? 4 : 0));
     }
     for (int i = 0; i < 2; i++) {
       for (int s = 0; s < TC_EPI_SETS; s++) ptx::mbar_init(&bar->d_full[s][i], 1);
       ptx::mbar_init(&bar->d_empty[i], 4);
     }
-    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], 1); }
+    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], TC_TMEM_A ? 4 : 1); }
+    for (int i = 0; i < TC_NTA; i++) { ptx::mbar_init(&bar->at_full[i], 4); ptx::mbar_init(&bar->at_empty[i], 1); }
     ptx::fence_barrier_init();
   }
   tc_fill_lut<NBITS>(s_lut, P.weights, tid, TC_THREADS);
@@ -376,7 +385,7 @@ k_maxsim_tc(TcParams P) {
   // Register budget per warpgroup (setmaxnreg sits at the top of each role's branch so ptxas
   // allocates per role): the epilogue keeps two TMEM load batches in flight, the rest need little.
   if (warp < 4) {
-  if constexpr (TC_EPI_SETS == 1) ptx::reg_dec<96>();
+  if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_dec<96>();
   if (warp == 0) {
     // ===== scheduler: candidate list, ring allocation and meta of every passage with >= 1 candidate =====
     const int64_t first = blockIdx.x, stride = gridDim.x;
@@ -478,9 +487,9 @@ k_maxsim_tc(TcParams P) {
     // word plus a constant, so a group costs a few dozen instructions.  The issuer is the serial
     // resource of the kernel: at N = 80 a group's 8 MMAs are only ~320 tensor clocks. =====
     if (ptx::elect_one()) {
-      const uint32_t a_lo0 = ((ptx::smem_u32(a_tile0) & 0x3ffffu) >> 4) | (1u << 16);   // descriptor low words: start
+      [[maybe_unused]] const uint32_t a_lo0 = ((ptx::smem_u32(a_tile0) & 0x3ffffu) >> 4) | (1u << 16);   // descriptor low words: start
       const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);    // address >> 4, LBO field = 1
-      constexpr uint32_t HI_A = (2048u >> 4) | (1u << 14) | (2u << 29);   // SBO 2048 | version 1 | SWIZZLE_128B
+      [[maybe_unused]] constexpr uint32_t HI_A = (2048u >> 4) | (1u << 14) | (2u << 29);   // SBO 2048 | version 1 | SWIZZLE_128B
       constexpr uint32_t HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024
       uint32_t st = 0, a_par = 0;        // query-tile stage / parity of its next a_full phase
       uint32_t ds = 0, d_par = 1;        // accumulator / parity of its next d_empty phase
@@ -499,8 +508,13 @@ k_maxsim_tc(TcParams P) {
         const int ngroups = (ncand + 3) >> 2;
         ptx::mbar_wait(&bar->b_full[slot], ph, 5);
         for (int g = 0; g < ngroups; g++) {
+#if TC_TMEM_A
+          ptx::mbar_wait(&bar->at_full[st], a_par, 6);                    // (st / a_par run over the TC_NTA tensor-memory stages here)
+          const uint32_t a_tmem = tmem_base + TC_A_COL0 + st * TC_A_TCOLS;
+#else
           ptx::mbar_wait(&bar->a_full[st], a_par, 6);
           const uint32_t a_lo = a_lo0 + st * (uint32_t)(TC_A_BYTES >> 4);
+#endif
           for (int c = 0; c < nchunk; c++) {
             ptx::mbar_wait(&bar->d_empty[ds], d_par, 7);
             ptx::tc_fence_after();
@@ -508,17 +522,25 @@ k_maxsim_tc(TcParams P) {
             const uint32_t b_lo = c ? b_lo1 : b_lo0, kb = c ? kb1 : kb0, idesc = c ? idesc1 : idesc0;
 #pragma unroll
             for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
-              const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
               const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
+#if TC_TMEM_A
+              ptx::mma_f16_ts(d_tmem, a_tmem + (uint32_t)k * 8u, db, idesc, k > 0 ? 1u : 0u);   // K = 16 step = 8 packed columns
+#else
+              const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
               ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+#endif
             }
+#if TC_TMEM_A
+            if (c == nchunk - 1) ptx::tc_commit(&bar->at_empty[st]);
+#else
             if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st]);
+#endif
             ptx::tc_commit(&bar->d_full[eset][ds]);
             ds ^= 1u;
             d_par ^= (ds == 0u) ? 1u : 0u;
           }
           if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
-          if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
+          if (++st == (uint32_t)(TC_TMEM_A ? TC_NTA : NA)) { st = 0; a_par ^= 1u; }
         }
         ptx::tc_commit(&bar->b_empty[slot]);   // arrives after the passage's last MMA retires
       }
@@ -528,7 +550,7 @@ k_maxsim_tc(TcParams P) {
     loader_role(warp - 2);
   }
   } else if (warp < TC_DEC_WARP0) {
-    if constexpr (TC_EPI_SETS == 1) ptx::reg_inc<176>();
+    if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_inc<176>();
     // ===== epilogue: TMEM -> max over tokens -> sum over query tokens -> pair list =====
     const int q4 = warp & 3;                // TMEM lane quarter == query slot inside the group
     const uint32_t myset = (uint32_t)(warp - 4) >> 2;   // this warp's set scores groups ug % TC_EPI_SETS == myset
@@ -580,7 +602,7 @@ k_maxsim_tc(TcParams P) {
           // max over the chunk's tokens == max over this thread's ncol TMEM columns; the load of
           // the next 32 columns is in flight while the current 32 are folded
           uint32_t ra[32], rt[16];
-          if constexpr (TC_EPI_SETS > 1) {
+          if constexpr (TC_EPI_SETS > 1 || TC_TMEM_A) {
             // two sets share the work: single-buffered loads keep a set inside the 96 registers every
             // warp of the 640-thread CTA gets (no setmaxnreg: the pool is only what the launch allocated)
 #pragma unroll 1
@@ -635,8 +657,61 @@ k_maxsim_tc(TcParams P) {
     }
     flush();
     flush();
+  } else if (TC_TMEM_A && warp >= TC_CONV_WARP0) {
+    // ===== converters (TC_TMEM_A): query tiles shared memory -> registers -> tensor memory.  Why: the tensor core
+    // fetches shared-memory operands at ~64 B/clk/SM (measured: every SS-mode MMA of this library takes
+    // (A bytes + B bytes) / 64 clocks -- 104 clocks for M = 128, N = 80 against 40 clocks of math), and the 4 KB A
+    // slice of every K-step is the bulk of it.  From tensor memory the A operand costs nothing, so the MMA of a
+    // group drops from ~830 to ~320 clocks.  The tiles still arrive by bulk copy (deep, latency-tolerant
+    // prefetch); warp j of this set owns TMEM lane quarter j = query j of the group: thread = one (query, token)
+    // row, which it reads out of the SWIZZLE_128B stage with sixteen conflict-free 16-byte loads (the 8 lanes
+    // of a quarter-warp sit on 8 different 16-byte bank groups by construction of the swizzle) and writes as
+    // the 64 packed columns of its lane with tcgen05.st. =====
+    const int j = warp - TC_CONV_WARP0;
+    const uint32_t a_lane = tmem_base + TC_A_COL0 + ((uint32_t)(j * 32) << 16);
+    // row `lane` of query j inside a stage: 8-row group lane >> 3 (2048 B apart), row lane & 7 (128 B), K-block 1024 B apart
+    const uint32_t row_off = (uint32_t)j * TC_Q_BYTES + (uint32_t)(lane >> 3) * 2048u + (uint32_t)(lane & 7) * 128u;
+    const uint32_t r7 = (uint32_t)lane & 7u;
+    uint32_t st = 0, a_par = 0;      // shared-memory stage / parity of its next a_full phase
+    uint32_t ts = 0, t_par = 1;      // tensor-memory stage / parity of its next at_empty phase
+    for (int e = 0;; e++) {
+      const int slot = e & (TC_NSLOT - 1);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 13);
+      const int ncand = meta[slot].ncand;
+      if (ncand < 0) break;
+      const int ngroups = (ncand + 3) >> 2;
+      for (int g = 0; g < ngroups; g++) {
+        const bool have = (TC_ABLATE & 1) ? (j == 0) : (g * 4 + j < ncand);   // a short last group leaves the other quarters stale (never read out)
+        ptx::mbar_wait(&bar->a_full[st], a_par, 14);
+        uint32_t r[64];
+        if (have) {
+          const uint8_t* src = a_tile0 + (size_t)st * TC_A_BYTES + row_off;
+#pragma unroll
+          for (int c = 0; c < 16; c++) {      // 16-byte chunk c & 7 of K-block c >> 3 sits at chunk (c & 7) ^ (row & 7)
+            const uint4 v = *reinterpret_cast<const uint4*>(src + (c >> 3) * 1024 + ((((uint32_t)c & 7u) ^ r7) << 4));
+            r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+          }
+        }
+        ptx::mbar_wait(&bar->at_empty[ts], t_par, 15);
+        ptx::tc_fence_after();
+        if (have) {
+          ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS, r);
+          ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS + 32, r + 32);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->a_empty[st]);   // the shared-memory stage is free: its loads have landed (tcgen05.st took the registers)
+        if (have) ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->at_full[ts]);
+        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
+        if (++ts == (uint32_t)TC_NTA) { ts = 0; t_par ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
+    }
   } else {
-    if constexpr (TC_EPI_SETS == 1) ptx::reg_dec<112>();
+    if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_dec<112>();
     if (warp < TC_DEC_FIRST) {
       loader_role(warp - TC_DEC_WARP0 + 2);
     } else {
