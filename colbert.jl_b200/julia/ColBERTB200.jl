@@ -25,9 +25,9 @@ function check(status::Int32)
     status == CB_OK && return nothing
     msg = last_error()
     status == CB_ERR_BAD_ARG && throw(DimensionMismatch(msg))      # ranking.jl:9-12, 71-74
-    status == CB_ERR_DOMAIN && throw(DomainError(status, msg))     # residual.jl:701-706, 763-768
+    status == CB_ERR_DOMAIN && throw(DomainError(msg))             # residual.jl:701-706, 763-768: DomainError("...") -- the message IS the payload
     status == CB_ERR_OOM && throw(OutOfMemoryError())
-    status == CB_ERR_BOUNDS && throw(BoundsError(msg))             # searching.jl:127
+    status == CB_ERR_BOUNDS && throw(ErrorException(msg))          # (a pid outside 1:N handed to a hook; `search` raises its own BoundsError below)
     error("libcolbert_b200 (status $status): $msg")                # CUDA / unsupported
 end
 
@@ -125,18 +125,23 @@ function search_batch_plaid(ix::ResidentIndex, Q::Array{Float32, 3}, k::Integer;
 end
 
 """
-    search(searcher, query, k)    # drop-in for src/searching.jl:93-128
+    ColBERTB200.search(searcher, query, k)    # drop-in for ColBERT.search, src/searching.jl:93-128
 
 Same return value and error behaviour as the reference: `(pids[1:k], scores[1:k])`, ties in
 ascending pid, `BoundsError` when fewer than `k` candidates exist (searching.jl:127).
+
+This module does NOT overwrite `ColBERT.search(::Searcher, ::String, ::Int)`: redefining a method another package
+owns is an error during precompilation since Julia 1.10 ("Method overwriting is not permitted during Module
+precompilation").  Either call `ColBERTB200.search`, or apply the one-line hook of INTEGRATION.md to
+src/searching.jl (`search(s, q, k) = ColBERTB200.search(s, q, k)` behind a `use_b200` flag of `ColBERTConfig`).
 """
-function ColBERT.search(searcher::Searcher, query::String, k::Int)
+function search(searcher::Searcher, query::String, k::Int)
     pids, scores = search(searcher, [query], k)
     pids[1], scores[1]
 end
 
 "Batched extension (the reference asserts one query per call, searching.jl:98)."
-function ColBERT.search(searcher::Searcher, queries::Vector{String}, k::Int)
+function search(searcher::Searcher, queries::Vector{String}, k::Int)
     Q = encode_queries(searcher.bert, searcher.linear, searcher.tokenizer, queries, searcher.config.dim,
         searcher.config.index_bsize, searcher.config.query_token, searcher.config.attend_to_mask_tokens,
         searcher.skiplist)
@@ -145,10 +150,11 @@ function ColBERT.search(searcher::Searcher, queries::Vector{String}, k::Int)
     search(searcher, Array{Float32, 3}(Q), k)
 end
 
-function ColBERT.search(searcher::Searcher, Q::Array{Float32, 3}, k::Int)
+function search(searcher::Searcher, Q::Array{Float32, 3}, k::Int)
     pids, scores, counts = search_batch(resident(searcher), Q, searcher.config.nprobe, k)
     for q in eachindex(counts)
-        counts[q] < k && throw(BoundsError(collect(1:counts[q]), 1:k))
+        # what `pids[indices][1:k]` throws upstream: BoundsError(<the candidate vector>, (1:k,))
+        counts[q] < k && throw(BoundsError(pids[1:counts[q], q], (1:k,)))
     end
     [pids[:, q] for q in axes(pids, 2)], [scores[:, q] for q in axes(scores, 2)]
 end
@@ -193,18 +199,63 @@ function maxsim(Q::Matrix{Float32}, D::Matrix{Float32}, pids::Vector{Int}, docle
     out
 end
 
+"`compress` (src/indexing/codecs/residual.jl:586-604); `bsize` is accepted and ignored."
+function compress(centroids::Matrix{Float32}, bucket_cutoffs::Vector{Float32}, dim::Int, nbits::Int,
+        embs::Matrix{Float32}; bsize::Int = 10000, device::Integer = 0)
+    n = size(embs, 2)
+    codes = zeros(UInt32, n)
+    residuals = Matrix{UInt8}(undef, div(dim, 8) * nbits, n)
+    GC.@preserve centroids bucket_cutoffs embs codes residuals check(ccall((:cb_compress, LIB), Int32,
+        (Int32, Int32, Int32, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Int64, Ptr{UInt32}, Ptr{UInt8}),
+        device, dim, nbits, size(centroids, 2), centroids, bucket_cutoffs, embs, n, codes, residuals))
+    codes, residuals
+end
+
+"""
+    ResidentIndex(index_path::String; device = 0, shard = 0, n_shards = 1)
+
+Opens the index directory the Indexer wrote (src/savers.jl) natively: the JLD2 files are mapped and uploaded by the
+library (cb_index_open), no host copy of the 20+ GB arrays is ever built (what `Searcher(index_path)` does at
+src/searching.jl:50-55).
+"""
+function ResidentIndex(index_path::String; device::Integer = 0, shard::Integer = 0, n_shards::Integer = 1)
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    base = Ref{Int64}(0)
+    check(ccall((:cb_index_open, LIB), Int32, (Ref{Ptr{Cvoid}}, Cstring, Int32, Int32, Int32, Ref{Int64}),
+        handle, index_path, device, shard, n_shards, base))
+    ResidentIndex(handle[], device, base[])
+end
+
 # ---- passage-sharded search over the GPUs of one box ----------------------------------------------
 """
-    ShardedIndex(searcher, n_gpus)
+    ShardedIndex(index_path, n_gpus)      # opens the shards from disk (cb_multi_open)
+    ShardedIndex(searcher, n_gpus)        # from the host arrays of a loaded Searcher
 
-Splits the passages into `n_gpus` contiguous ranges balanced by embedding count and uploads one
-shard per device (the IVF of each shard is rebuilt on its device from the shard's codes, with
-`_build_ivf` semantics).  `search_batch` scores every shard and merges the per-shard top-k lists
-with `cb_merge_topk` -- (score desc, pid asc), the order of the reference's stable `sortperm`.
-(One Julia process driving all devices; the torchrun/NCCL variant is bench.py + sharding.py.)
+The passages are split into `n_gpus` contiguous ranges balanced by embedding count, one shard per device (each
+shard's IVF is rebuilt on its device from its codes, `_build_ivf` semantics).  `search_batch` is ONE ccall
+(cb_multi_search_batch): this Julia thread drives all devices -- queries uploaded once and forwarded over NVLink,
+stage 1 split by query, every device scoring its range concurrently, the per-shard top-k lists merged on the first
+device by (score desc, pid asc), the order of the reference's stable `sortperm`.  No process per GPU, no NCCL.
 """
-struct ShardedIndex
-    shards::Vector{ResidentIndex}
+mutable struct ShardedIndex
+    handle::Ptr{Cvoid}
+    shards::Vector{ResidentIndex}        # kept alive (borrowed by the group); empty when the library owns them
+    function ShardedIndex(handle, shards)
+        sx = new(handle, shards)
+        finalizer(sx) do x
+            if x.handle != C_NULL
+                ccall((:cb_multi_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle)
+                x.handle = C_NULL
+            end
+        end
+        sx
+    end
+end
+
+function ShardedIndex(index_path::String, n_gpus::Integer)
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cb_multi_open, LIB), Int32, (Ref{Ptr{Cvoid}}, Cstring, Int32, Ptr{Int32}), handle, index_path, n_gpus, C_NULL))
+    ShardedIndex(handle[], ResidentIndex[])
 end
 
 function ShardedIndex(s::Searcher, n_gpus::Integer)
@@ -231,24 +282,20 @@ function ShardedIndex(s::Searcher, n_gpus::Integer)
             pointer(codes), pointer(residuals), pointer(doclens), C_NULL, C_NULL, lo, 0))
         push!(shards, ResidentIndex(handle[], r - 1, lo))
     end
-    ShardedIndex(shards)
+    group = Ref{Ptr{Cvoid}}(C_NULL)
+    handles = [ix.handle for ix in shards]
+    GC.@preserve handles check(ccall((:cb_multi_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Ptr{Ptr{Cvoid}}), group, n_gpus, handles))
+    ShardedIndex(group[], shards)
 end
 
 function search_batch(sx::ShardedIndex, Q::Array{Float32, 3}, nprobe::Integer, k::Integer)
-    n = length(sx.shards)
-    nq = size(Q, 3)
-    all_p = zeros(Int64, k, nq, n)
-    all_s = fill(-Inf32, k, nq, n)
-    counts = zeros(Int32, nq)
-    for (r, ix) in enumerate(sx.shards)
-        p, s, c = search_batch(ix, Q, nprobe, k)
-        all_p[:, :, r] = p; all_s[:, :, r] = s; counts .+= c
-    end
+    dim, T, nq = size(Q)
     pids = zeros(Int64, k, nq)
-    scores = zeros(Float32, k, nq)
-    GC.@preserve all_p all_s pids scores check(ccall((:cb_merge_topk, LIB), Int32,
-        (Int32, Int32, Int32, Int32, Ptr{Int64}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}),
-        0, n, nq, k, all_p, all_s, pids, scores))
+    scores = fill(-Inf32, k, nq)
+    counts = zeros(Int32, nq)
+    GC.@preserve Q pids scores counts check(ccall((:cb_multi_search_batch, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Int32, Int32, Int32, Int32, Ptr{Int64}, Ptr{Float32}, Ptr{Int32}),
+        sx.handle, Q, nq, T, nprobe, k, pids, scores, counts))
     pids, scores, counts
 end
 
