@@ -181,6 +181,7 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, o));   // oracle.tree_sum32
       if (m > 0.f) {      // warp-uniform: every lane holds the same sum
+        __syncwarp();     // every lane is done reading s_hit[..][>= i] of this round before slot nemit <= i is reused
         if (lane == 0) { s_hit[wi][nemit] = cb_orderable(m); s_eq[wi][nemit] = (uint16_t)q; }
         nemit++;
       }

@@ -126,6 +126,7 @@ __device__ __noinline__ S1State s1_compact(uint32_t mask, float* bv, int32_t* bi
     mask &= mask - 1;
     const int n = __shfl_sync(0xffffffffu, cnt, L);
     const int row = rowbase + L;
+    __syncwarp();   // lane L's appends (plain shared-memory stores) become visible to the lanes that read its row below
     const int a = s1_slot(row, lane);
     const float v = lane < n ? bv[a] : -INFINITY;
     const int32_t id = lane < n ? bi[a] : 0x7fffffff;
@@ -135,7 +136,7 @@ __device__ __noinline__ S1State s1_compact(uint32_t mask, float* bv, int32_t* bi
       const float vk = __shfl_sync(0xffffffffu, v, k);
       rank += (vk > v || (vk == v && k < lane)) ? 1 : 0;
     }
-    // (every lane has read its slot before the first shuffle completed: the stores below cannot race the loads)
+    __syncwarp();   // every lane has read its slot: the stores below may now reuse them
     if (rank < CB_TOPR) { const int wa = s1_slot(row, rank); bv[wa] = v; bi[wa] = id; }
     const uint32_t who = __ballot_sync(0xffffffffu, rank == CB_TOPR - 1);
     const float t16 = __shfl_sync(0xffffffffu, v, who ? __ffs(who) - 1 : 0);

@@ -49,7 +49,10 @@ constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first decompression warp
 constexpr int TC_DIM = 128, TC_T = 32;
 constexpr int TC_MAX_BROWS = TC_TMEM_A ? 192 : 240;   // rows (tokens) per chunk; multiple of 16, <= TC_D_COLS TMEM columns
 constexpr int TC_MAX_ASTAGES = 6;
-constexpr int TC_NSLOT = 4;            // passage entries in flight (meta slots == tile barriers)
+#ifndef TC_NSLOT_LOG2
+#define TC_NSLOT_LOG2 2
+#endif
+constexpr int TC_NSLOT = 1 << TC_NSLOT_LOG2;   // passage entries in flight (meta slots == tile barriers)
 constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 128 x fp16
 constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 #ifndef TC_ABLATE
@@ -143,11 +146,15 @@ __device__ __forceinline__ Bits16<NBITS> load_bits16(const uint8_t* __restrict__
 // entry is replicated across the 128-byte bank row (entry e of byte b for replica r at
 // b*128 + r*entry_bytes), and a lane reads replica lane % replicas, so the lanes that share one
 // shared-memory wavefront always hit different banks whatever bytes they hold: no bank conflicts.
+#ifndef TC_LUT_ROW
+#define TC_LUT_ROW 128                  // bytes per table row (entry replicated TC_LUT_ROW / entry size times): 128 = no bank conflicts at all
+#endif
 template <int NBITS> struct LutGeom {
   static constexpr int ENTRY_BYTES = 16 / NBITS;          // 8/NBITS fp16 weights
-  static constexpr int REPLICAS = 128 / ENTRY_BYTES;      // 8, 16, 32
+  static constexpr int REPLICAS = (TC_LUT_ROW / ENTRY_BYTES) > 0 ? (TC_LUT_ROW / ENTRY_BYTES) : 1;      // 8, 16, 32 at 128-byte rows
+  static constexpr int ROW = REPLICAS * ENTRY_BYTES;
 };
-constexpr int TC_LUT_BYTES = 256 * 128;
+constexpr int TC_LUT_BYTES = 256 * TC_LUT_ROW;
 template <int NBITS>
 __device__ __forceinline__ void lookup_weights16(const uint8_t* __restrict__ lut_lane, const Bits16<NBITS>& b, __half2 (&w)[8]) {
   // lut_lane = table + (lane % replicas) * entry_bytes; w[0..3] = dims 8*l8.., w[4..7] = dims 64+8*l8..
@@ -155,19 +162,19 @@ __device__ __forceinline__ void lookup_weights16(const uint8_t* __restrict__ lut
   for (int h = 0; h < 2; h++) {
     const uint32_t bits = h ? b.hi : b.lo;
     if constexpr (NBITS == 1) {
-      const uint4 x = *reinterpret_cast<const uint4*>(lut_lane + (bits & 255u) * 128u);
+      const uint4 x = *reinterpret_cast<const uint4*>(lut_lane + (bits & 255u) * (uint32_t)LutGeom<NBITS>::ROW);
       w[4 * h] = *reinterpret_cast<const __half2*>(&x.x); w[4 * h + 1] = *reinterpret_cast<const __half2*>(&x.y);
       w[4 * h + 2] = *reinterpret_cast<const __half2*>(&x.z); w[4 * h + 3] = *reinterpret_cast<const __half2*>(&x.w);
     } else if constexpr (NBITS == 2) {
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        const uint2 x = *reinterpret_cast<const uint2*>(lut_lane + ((bits >> (8 * j)) & 255u) * 128u);
+        const uint2 x = *reinterpret_cast<const uint2*>(lut_lane + ((bits >> (8 * j)) & 255u) * (uint32_t)LutGeom<NBITS>::ROW);
         w[4 * h + 2 * j] = *reinterpret_cast<const __half2*>(&x.x); w[4 * h + 2 * j + 1] = *reinterpret_cast<const __half2*>(&x.y);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(lut_lane + ((bits >> (8 * j)) & 255u) * 128u);
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(lut_lane + ((bits >> (8 * j)) & 255u) * (uint32_t)LutGeom<NBITS>::ROW);
         w[4 * h + j] = *reinterpret_cast<const __half2*>(&x);
       }
     }
@@ -242,7 +249,7 @@ __device__ __forceinline__ void tc_fill_lut(uint8_t* s_lut, const float* __restr
   constexpr int DPB = 8 / NBITS, REP = LutGeom<NBITS>::REPLICAS;
   for (int i = tid; i < 256 * REP * DPB; i += nthreads) {
     const int j = i % DPB, r = (i / DPB) % REP, byte = i / (DPB * REP);
-    reinterpret_cast<__half*>(s_lut + byte * 128 + r * LutGeom<NBITS>::ENTRY_BYTES)[j] =
+    reinterpret_cast<__half*>(s_lut + byte * LutGeom<NBITS>::ROW + r * LutGeom<NBITS>::ENTRY_BYTES)[j] =
         __float2half_rn(weights[(byte >> (j * NBITS)) & ((1 << NBITS) - 1)]);
   }
 }
@@ -353,7 +360,7 @@ k_maxsim_tc(TcParams P) {
     uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 8);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 8);
       const Meta& m = meta[slot];
       const int ncand = m.ncand;
       if (ncand < 0) break;
@@ -439,7 +446,7 @@ k_maxsim_tc(TcParams P) {
       const uint32_t bytes = (uint32_t)(n0 + n1) * 256u;
       // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_empty[slot], ((e >> 2) & 1) ^ 1, 1);
+      ptx::mbar_wait(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
       if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
       // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps.  The
       // regions of the last TC_NSLOT entries sit in shared memory (dynamically indexed local arrays
@@ -456,7 +463,7 @@ k_maxsim_tc(TcParams P) {
           if (off < s_region[2 * sj + 1] && s_region[2 * sj] < off + bytes && need < ej + 1) need = ej + 1;
         }
       }
-      for (; tail < need; tail++) ptx::mbar_wait(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> 2) & 1, 2);
+      for (; tail < need; tail++) ptx::mbar_wait(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> TC_NSLOT_LOG2) & 1, 2);
       __syncwarp();
       if (lane == 0) { s_region[2 * slot] = off; s_region[2 * slot + 1] = off + bytes; }
       __syncwarp();
@@ -479,7 +486,7 @@ k_maxsim_tc(TcParams P) {
     }
     // end of stream
     const int slot = e & (TC_NSLOT - 1);
-    ptx::mbar_wait(&bar->meta_empty[slot], ((e >> 2) & 1) ^ 1, 3);
+    ptx::mbar_wait(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 3);
     if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
   } else if (warp == 1) {
     // ===== MMA issuer: ONE elected thread runs the whole loop (no per-group elect / reconvergence);
@@ -496,7 +503,7 @@ k_maxsim_tc(TcParams P) {
       uint32_t eset = 0;                 // epilogue set that consumes the next group
       for (int e = 0;; e++) {
         const int slot = e & (TC_NSLOT - 1);
-        const uint32_t ph = (e >> 2) & 1;
+        const uint32_t ph = (e >> TC_NSLOT_LOG2) & 1;
         ptx::mbar_wait(&bar->meta_full[slot], ph, 4);
         const int ncand = meta[slot].ncand;
         if (ncand < 0) break;
@@ -579,7 +586,7 @@ k_maxsim_tc(TcParams P) {
     };
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 10);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 10);
       const Meta& m = meta[slot];
       const int ncand = m.ncand;
       if (ncand < 0) break;
@@ -676,7 +683,7 @@ k_maxsim_tc(TcParams P) {
     uint32_t ts = 0, t_par = 1;      // tensor-memory stage / parity of its next at_empty phase
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> 2) & 1, 13);
+      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 13);
       const int ncand = meta[slot].ncand;
       if (ncand < 0) break;
       const int ngroups = (ncand + 3) >> 2;
@@ -733,7 +740,7 @@ k_maxsim_tc(TcParams P) {
       bool stop = false;
       for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
         const int sl = ee & (TC_NSLOT - 1);
-        ptx::mbar_wait(&bar->meta_full[sl], (ee >> 2) & 1, 12, 20);
+        ptx::mbar_wait(&bar->meta_full[sl], (ee >> TC_NSLOT_LOG2) & 1, 12, 20);
         if (meta[sl].ncand < 0) { stop = true; break; }
         if (ee != e) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[sl]); }
       }

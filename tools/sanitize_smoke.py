@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import colbert_jl_b200 as cb  # noqa: E402
 from colbert_jl_b200 import synthetic as S  # noqa: E402
 
-ix = S.make_index(400, 256, seed=5, doclen_mean=60, doclen_std=40, doclen_min=1, doclen_max=300)
+ix = S.make_index(400, 2048, seed=5, doclen_mean=60, doclen_std=40, doclen_min=1, doclen_max=300)
 Q = S.make_queries(ix["centroids"], 6, seed=6)
 Qj = np.transpose(Q, (2, 1, 0))
 cfg = cb.ColBERTConfig(dim=128, nbits=2, nprobe=2, query_maxlen=32)
@@ -20,7 +20,7 @@ with cb.Searcher(cfg, ix["centroids"].T, None, ix["bucket_weights"], ix["ivf"], 
     s.retrieve(Q[0].T)
     s.probe(Qj)
     s.score_pids(Q[0].T, p[0])
-    s.search_batch_plaid(Qj, 5, ncells=3, centroid_score_threshold=0.3, ndocs=50)
+    s.search_batch_plaid(Qj, 5, ncells=2, centroid_score_threshold=0.6, ndocs=50)
     s.set_option("force_generic", 1)
     s.set_option("stage1_impl", 1)
     p2, sc2, _ = s.search_batch(Qj, 5)                     # SIMT stage 1 + generic scoring kernel
