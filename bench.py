@@ -560,6 +560,15 @@ def main():
 
     ms_per_step, clocks = leg.timed(args.steps, args.warmup, sample_clocks=True)
     value = nq / (ms_per_step * 1e-3)
+    if os.environ.get("CB_TC_PROF_OUT") and hasattr(lib, "cb_debug_tc_prof"):   # -DTC_PROF=1 measurement builds only (tools/tc_wait_profile.py)
+        import ctypes as C
+        import numpy as _np
+        _buf = _np.zeros((160, 32, 24), dtype=_np.uint64)
+        lib.cb_debug_tc_prof(_buf.ctypes.data_as(C.c_void_p))
+        _np.save(os.environ["CB_TC_PROF_OUT"], _buf)
+        _tr = _np.zeros((12, 4096), dtype=_np.int64)
+        lib.cb_debug_tc_trace(_tr.ctypes.data_as(C.c_void_p))
+        _np.save(os.environ["CB_TC_PROF_OUT"].replace(".npy", "_trace.npy"), _tr)
     # kernels launched by this rank's library per step (+ the all-gathers / merge of the sharded path)
     launches = int(s.stat("launches")) + (3 if world > 1 else 0)
     pairs, pair_embs = s.stat("pairs"), s.stat("pair_embeddings")

@@ -32,6 +32,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (no hardware suspend, unlike try_wait)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Wait for a phase of an mbarrier.  `mbarrier.try_wait` suspends the thread in hardware for a
 // system-dependent time before it reports failure, so the loop is not a busy spin; `backoff_ns` > 0
 // additionally makes a waiting warp sleep between polls so that roles with slack (e.g. the

@@ -44,10 +44,37 @@ namespace {
 #ifndef TC_TMEM_A
 #define TC_TMEM_A 0                    // 1 = the A operand (query tiles) is forwarded shared memory -> registers -> TENSOR MEMORY by
 #endif                                 // four converter warps and tcgen05.mma reads it from there (see "what bounds it" above); 0 = A from shared memory
+#ifndef TC_LANES
+#define TC_LANES 1                     // 2 = the two-lane kernel k_maxsim_tc2 (two MMA issuers, A operand in tensor memory, fused convert + epilogue workers)
+#endif
+#ifndef TC_EPI_MODE
+#define TC_EPI_MODE ((TC_EPI_SETS > 1) ? 0 : 1)   // accumulator read-out: 0 = one 32-column load at a time, 1 = double-buffered, 2 = all loads of up to
+#endif                                              // 80 columns issued at once, ONE tcgen05.wait::ld, accumulator released before the fold
+// Register budget per warpgroup (setmaxnreg; 0 = leave the launch allocation).  The pool is threads x launch registers:
+// 512 x 128 (shared-memory A) or 640 x 96 (TC_TMEM_A); a budget must sum to at most that over the warpgroups.
+#ifndef TC_REG_CTRL
+#if TC_EPI_SETS == 1 && !TC_TMEM_A
+#define TC_REG_CTRL 96
+#define TC_REG_EPI 176
+#define TC_REG_DEC 112
+#define TC_REG_CONV 0
+#elif TC_EPI_SETS == 1 && TC_TMEM_A
+#define TC_REG_CTRL 56
+#define TC_REG_EPI 136
+#define TC_REG_DEC 0
+#define TC_REG_CONV 0
+#else
+#define TC_REG_CTRL 0
+#define TC_REG_EPI 0
+#define TC_REG_DEC 0
+#define TC_REG_CONV 0
+#endif
+#endif
 constexpr int TC_NEPI_WARPS = 4 * TC_EPI_SETS;
 constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first decompression warp
 constexpr int TC_DIM = 128, TC_T = 32;
-constexpr int TC_MAX_BROWS = TC_TMEM_A ? 192 : 240;   // rows (tokens) per chunk; multiple of 16, <= TC_D_COLS TMEM columns
+constexpr int TC_MAX_BROWS = (TC_LANES == 2) ? 128 : (TC_TMEM_A ? 192 : 240);   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
+constexpr int TC_MAX_CHUNKS = (TC_LANES == 2) ? 3 : 2;                          // chunks per passage (accumulator passes per group)
 constexpr int TC_MAX_ASTAGES = 6;
 #ifndef TC_NSLOT_LOG2
 #define TC_NSLOT_LOG2 2
@@ -69,10 +96,42 @@ constexpr int TC_DEC_FIRST = TC_DEC_WARP0 + (TC_NLOAD - 2);   // first decompres
 constexpr int TC_NTEAMS = TC_NTEAMS_;   // decompression teams (round-robin over passages)
 constexpr int TC_CONV_WARP0 = TC_DEC_FIRST + TC_NDEC_WARPS;   // converter warps (TC_TMEM_A): one per TMEM lane quarter
 constexpr int TC_THREADS = 32 * (TC_CONV_WARP0 + (TC_TMEM_A ? 4 : 0));
+constexpr int TC_LAUNCH_REGS = (65536 / TC_THREADS) & ~7;   // what __launch_bounds__(TC_THREADS, 1) lets ptxas give every thread
+template <int N> __device__ __forceinline__ void tc_reg_budget() {   // a role's setmaxnreg (whole warpgroup); 0 = keep the launch allocation
+  if constexpr (N > TC_LAUNCH_REGS) ptx::reg_inc<N>();
+  else if constexpr (N > 0 && N < TC_LAUNCH_REGS) ptx::reg_dec<N>();
+}
 // tensor memory: two accumulators of TC_D_COLS fp32 columns; with TC_TMEM_A also TC_NTA query-tile stages of 64 columns
 // (128 lanes x 128 fp16 = 64 packed 32-bit columns: lane = (query, token) row, column j = dims 2j, 2j+1)
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = TC_TMEM_A ? 192 : 256, TC_A_COL0 = 2 * TC_D_COLS, TC_A_TCOLS = 64;
 constexpr int TC_NTA = 2;
+
+// Measurement-only build (-DTC_PROF=1): every mbarrier wait is timed with clock64 and charged to (warp, wait tag); slot 0 of a
+// warp holds the clocks of its whole role loop.  Read back with cb_debug_tc_prof (tools/tc_wait_profile.py).
+#ifndef TC_PROF
+#define TC_PROF 0
+#endif
+#if TC_PROF
+__device__ unsigned long long g_tc_prof[160 * 32 * 24];
+__shared__ unsigned long long s_prof[32 * 24];
+#define TCW(bar_, par_, tag_, ...)                                                          \
+  do {                                                                                      \
+    const long long t0_ = clock64();                                                        \
+    ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__);                                        \
+    if (lane == 0 || warp == 1) s_prof[warp * 24 + (tag_)] += (unsigned long long)(clock64() - t0_);   \
+  } while (0)
+// event trace of CTA 0 (steady state: groups TC_TRACE_G0 .. +4095): g_tc_trace[event][group] = clock64
+constexpr int TC_TRACE_G0 = 20000, TC_TRACE_N = 4096;
+__device__ long long g_tc_trace[12 * TC_TRACE_N];
+#define TCT(ev_, g_) do { if (blockIdx.x == 0 && (lane == 0 || warp == 1) && (g_) >= TC_TRACE_G0 && (g_) < TC_TRACE_G0 + TC_TRACE_N) g_tc_trace[(ev_) * TC_TRACE_N + (g_) - TC_TRACE_G0] = clock64(); } while (0)
+#define TCP_BEGIN() const long long tp0_ = clock64()
+#define TCP_END(tag_) do { if (lane == 0 || warp == 1) s_prof[warp * 24 + (tag_)] += (unsigned long long)(clock64() - tp0_); } while (0)
+#else
+#define TCW(bar_, par_, tag_, ...) ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__)
+#define TCP_BEGIN() do {} while (0)
+#define TCP_END(tag_) do {} while (0)
+#define TCT(ev_, g_) do {} while (0)
+#endif
 
 struct Meta {            // one passage entry, written by the scheduler
   int ncand;             // candidate queries of the passage (< 0: end of stream)
@@ -91,6 +150,8 @@ struct Barriers {
   uint64_t a_full[TC_MAX_ASTAGES], a_empty[TC_MAX_ASTAGES];
   uint64_t d_full[TC_EPI_SETS][2], d_empty[2];
   uint64_t at_full[TC_NTA], at_empty[TC_NTA];   // query-tile stages in tensor memory (TC_TMEM_A)
+  uint64_t l_afull[2][2], l_dempty[2], l_dfull[2];   // two-lane kernel: lane's A tile t holds a group / accumulator drained / MMAs retired
+  uint64_t t2_afull[2][TC_MAX_ASTAGES], t2_aempty[2][TC_MAX_ASTAGES];   // two-lane kernel: bulk-copy stage barriers PER LANE (see t2_loader_role)
 };
 
 struct TcParams {
@@ -113,6 +174,17 @@ __device__ __forceinline__ void fold32(const uint32_t (&r)[32], float& m0, float
   }
 }
 __device__ __forceinline__ void fold16(const uint32_t (&r)[16], float& m0, float& m1, float& m2, float& m3) {
+  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])));
+  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])));
+  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])));
+  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])));
+  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+}
+
+__device__ __forceinline__ void fold16_lo(const uint32_t (&r)[32], float& m0, float& m1, float& m2, float& m3) {
   m0 = fmaxf(m0, fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])));
   m1 = fmaxf(m1, fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
   m2 = fmaxf(m2, fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])));
@@ -232,16 +304,18 @@ __device__ __forceinline__ void finish_token16(const uint8_t* __restrict__ lut_l
   }
 }
 
-// Operand-tile geometry of a passage of L tokens: one chunk of n0 rows (L padded to 16), or two
-// balanced chunks when L > TC_MAX_BROWS (two accumulators, one running maximum).
+// Operand-tile geometry of a passage of L tokens: one chunk of n0 rows (L padded to 16), or nchunk <= TC_MAX_CHUNKS balanced
+// chunks when L > TC_MAX_BROWS -- chunks 0 .. nchunk-2 have n0 rows, the last one n1 (one accumulator pass each, one running
+// maximum).  n1 = 0 for a single chunk.
 __device__ __forceinline__ void tc_tile_geometry(int L, int& nchunk, int& n0, int& n1) {
   nchunk = 1; n0 = (L + 15) & ~15; n1 = 0;
   if (L > TC_MAX_BROWS) {
-    nchunk = 2;
-    n0 = (((L + 1) >> 1) + 15) & ~15;
-    n1 = (L - n0 + 15) & ~15;
+    nchunk = (L + TC_MAX_BROWS - 1) / TC_MAX_BROWS;
+    n0 = (((L + nchunk - 1) / nchunk) + 15) & ~15;
+    n1 = (L - (nchunk - 1) * n0 + 15) & ~15;
   }
 }
+__device__ __forceinline__ int tc_total_rows(int nchunk, int n0, int n1) { return nchunk == 1 ? n0 : (nchunk - 1) * n0 + n1; }
 
 // byte -> bucket weights table (fp16, every entry replicated across its 128-byte bank row)
 template <int NBITS>
@@ -254,7 +328,10 @@ __device__ __forceinline__ void tc_fill_lut(uint8_t* s_lut, const float* __restr
   }
 }
 
-constexpr int TC_DBATCH = 5;
+#ifndef TC_DBATCH_
+#define TC_DBATCH_ 5
+#endif
+constexpr int TC_DBATCH = TC_DBATCH_;   // decompression rounds whose loads are all in flight at once
 constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
 
 // One team warp's share of a passage: packed codes/residuals -> normalised fp16 operand tile(s) in shared
@@ -262,11 +339,10 @@ constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
 // decompression role and, unchanged, by the parity hook kernel k_tc_dump (DUMP = true).
 template <int NBITS, bool DUMP>
 __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const uint8_t* __restrict__ lut_lane, int dw, int lane,
-                                                      int L, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out) {
+                                                      int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out) {
   constexpr int TEAM_WARPS = TC_TEAM_WARPS;
   const int l8 = lane & 7;
-  uint8_t* tile1 = tile0 + n0 * 256;
-  const int nrows = n0 + n1;                                    // operand rows (multiple of 16)
+  const int nrows = tc_total_rows(nchunk, n0, n1);              // operand rows (multiple of 16)
   // operand row of this lane in round j: rr = 4 * (dw + TEAM_WARPS * j) + (lane >> 3)
   const int rr0 = 4 * dw + (lane >> 3);
   const int nround = (nrows - 4 * dw + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);   // warp-uniform
@@ -301,11 +377,198 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
     for (int i = 0; i < TC_DBATCH; i++) {
       if (i < per && j0 + i < nround) {   // warp-uniform
         const int rr = rr0 + 4 * TEAM_WARPS * (j0 + i);
-        const int c = rr >= n0 ? 1 : 0;
-        finish_token16<NBITS, DUMP>(lut_lane, bits[i], cr[i], l8, c ? tile1 : tile0, (c ? n1 : n0) * 128, rr - c * n0,
+        const int c = (rr >= n0 ? 1 : 0) + (rr >= 2 * n0 ? 1 : 0);        // chunk of this row (nchunk <= 3)
+        finish_token16<NBITS, DUMP>(lut_lane, bits[i], cr[i], l8, tile0 + c * n0 * 256, ((nchunk > 1 && c == nchunk - 1) ? n1 : n0) * 128, rr - c * n0,
                                     (DUMP && rr < L) ? raw_out + (size_t)rr * TC_DIM : nullptr);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roles shared by the scoring kernels (k_maxsim_tc and the two-lane k_maxsim_tc2)
+// ---------------------------------------------------------------------------------------------
+struct TcCtx {           // the CTA's shared-memory carve-up
+  uint8_t* ring; uint8_t* a_tile0; Meta* meta; Barriers* bar; uint32_t* s_region; uint8_t* s_lut; int NA;
+};
+
+// ===== query-tile loaders: EVERY loader serves EVERY group, loader li fetching the group's queries
+// j = li, li + NLOAD, ...  One warp sustains only ~31 B/clk of 8 KB bulk copies (a copy occupies
+// its issuing warp for ~270 clocks: tools/l2_to_sm_ceiling.cu, profiles/r02_l2_to_sm_ceiling.txt),
+// while the L2 -> SM path itself carries 76 B/clk/SM; spreading one group's four copies over
+// several issuers shortens the fill time of a stage. =====
+template <int NLOAD>
+__device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S, const int li, const int warp, const int lane) {
+  Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const a_tile0 = S.a_tile0; const int NA = S.NA;
+  (void)warp;
+  uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
+  [[maybe_unused]] int gc = 0;
+  for (int e = 0;; e++) {
+    const int slot = e & (TC_NSLOT - 1);
+    TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 8);
+    const Meta& m = meta[slot];
+    const int ncand = m.ncand;
+    if (ncand < 0) break;
+    const int ngroups = (ncand + 3) >> 2;
+    for (int g = 0; g < ngroups; g++) {
+      const uint32_t st_g = st, par_g = a_par;
+      if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
+      TCW(&bar->a_empty[st_g], par_g, 9);
+      if (li == 0) TCT(6, gc);
+      gc++;
+      const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
+      uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
+      const int nmine = (nqg - li + NLOAD - 1) / NLOAD;      // queries li, li + NLOAD, ... < nqg
+      if (nmine <= 0) {
+        if (ptx::elect_one()) ptx::mbar_arrive(&bar->a_full[st_g]);
+        continue;
+      }
+      const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * NLOAD] : 0;   // lane i holds this loader's i-th query
+      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nmine * TC_Q_BYTES);
+      for (int i = 0; i < nmine; i++) {
+        const int q = __shfl_sync(0xffffffffu, qv, i);
+        if (ptx::elect_one())
+          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
+  }
+}
+
+// ===== scheduler: candidate list, ring allocation and meta of every passage with >= 1 candidate =====
+__device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx& S, const int warp, const int lane) {
+  Barriers* const bar = S.bar; Meta* const meta = S.meta; uint32_t* const s_region = S.s_region;
+  (void)warp;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  uint32_t head = 0;             // next free byte of the ring
+  int e = 0;                     // entry counter
+  int tail = 0;                  // entries < tail are known to have released their tile
+  // Everything the scheduler reads from global memory for passage p -- its extent, its bitmap words
+  // and the extent of the passage whose packed bytes it will prefetch -- is requested TWO
+  // iterations ahead and carried in registers, so no global latency sits on the per-passage path
+  // (one exposed L2/HBM round trip per passage made the scheduler the bottleneck of the kernel at
+  // ~17 candidates per passage: nothing downstream ever saw a full pipeline).
+  struct Hdr { int64_t o0, o1, f0, f1, p; uint32_t w; };
+  // With a passage list (sparse bitmap) item i is passage pid_list[i]: the pid is requested one more
+  // iteration ahead than the header that depends on it.  (No packed-byte prefetch in that mode.)
+  const int64_t n_items = P.pid_list ? P.n_list : P.Np;
+  auto pid_of = [&](int64_t i) -> int64_t { return (P.pid_list && i < n_items) ? (int64_t)P.pid_list[i] : i; };
+  auto load_hdr = [&](int64_t i, int64_t p) {
+    Hdr h; h.o0 = h.o1 = h.f0 = h.f1 = 0; h.w = 0u; h.p = p;
+    if (i < n_items) {
+      h.o0 = P.offsets[p]; h.o1 = P.offsets[p + 1];
+      h.w = (lane < P.W) ? P.bitmap[p * P.W + lane] : 0u;
+      const int64_t pf = p + 6 * stride;       // pull its packed bytes from HBM into L2 a few passages ahead
+      if (!P.pid_list && pf < P.Np) { h.f0 = P.offsets[pf]; h.f1 = P.offsets[pf + 1]; }
+    }
+    return h;
+  };
+  Hdr h1 = load_hdr(first, pid_of(first)), h2 = load_hdr(first + stride, pid_of(first + stride));
+  int64_t pq = pid_of(first + 2 * stride);
+  for (int64_t it = first; it < n_items; it += stride) {
+    const Hdr h = h1;
+    h1 = h2;
+    const int64_t pq_next = pid_of(it + 3 * stride);
+    h2 = load_hdr(it + 2 * stride, pq);
+    pq = pq_next;
+    const int64_t p = h.p;
+    const int64_t e0 = h.o0;
+    const int L = (int)(h.o1 - h.o0);
+    uint32_t w = h.w;
+    if (h.f1 > h.f0) {
+      const char* r0 = reinterpret_cast<const char*>(P.residuals) + h.f0 * P.R;
+      const char* c0 = reinterpret_cast<const char*>(P.codes) + h.f0 * 4;
+      const int64_t rbytes = (h.f1 - h.f0) * P.R, cbytes = (h.f1 - h.f0) * 4;
+      for (int64_t o = (int64_t)lane * 128; o < rbytes; o += 32 * 128) ptx::prefetch_l2(r0 + o);
+      for (int64_t o = (int64_t)lane * 128; o < cbytes; o += 32 * 128) ptx::prefetch_l2(c0 + o);
+    }
+    if (L <= 0 || L > P.long_limit) w = 0u;          // empty, or too long: the generic kernel scores it
+    if (!__any_sync(0xffffffffu, w != 0u)) continue;  // no query of the batch wants this passage
+    // tile geometry
+    int nchunk, n0, n1;
+    tc_tile_geometry(L, nchunk, n0, n1);
+    const uint32_t bytes = (uint32_t)tc_total_rows(nchunk, n0, n1) * 256u;
+    // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
+    const int slot = e & (TC_NSLOT - 1);
+    TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
+    if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
+    // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps.  The
+    // regions of the last TC_NSLOT entries sit in shared memory (dynamically indexed local arrays
+    // would live in local memory, and with the whole carve-out given to shared memory there is no
+    // L1 to hold them)
+    uint32_t off = head;
+    if (off + bytes > (uint32_t)P.ring_bytes) off = 0;
+    int need = tail;             // entries < need must be free
+#pragma unroll
+    for (int j = 1; j < TC_NSLOT; j++) {
+      const int ej = e - j;
+      if (ej >= tail) {
+        const int sj = ej & (TC_NSLOT - 1);
+        if (off < s_region[2 * sj + 1] && s_region[2 * sj] < off + bytes && need < ej + 1) need = ej + 1;
+      }
+    }
+    for (; tail < need; tail++) TCW(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> TC_NSLOT_LOG2) & 1, 2);
+    __syncwarp();
+    if (lane == 0) { s_region[2 * slot] = off; s_region[2 * slot + 1] = off + bytes; }
+    __syncwarp();
+    head = off + bytes;
+    // candidate list
+    Meta& m = meta[slot];
+    const int c = __popc(w);
+    int pre = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+    int base = pre - c;
+    while (w) { const int b = __ffs(w) - 1; w &= w - 1; m.q[base++] = (uint16_t)(lane * 32 + b); }
+    const int ncand = __shfl_sync(0xffffffffu, pre, 31);
+    if (lane == 0) {
+      m.ncand = ncand; m.L = L; m.nchunk = nchunk; m.n0 = n0; m.n1 = n1; m.pid = (int)p; m.b_off = off; m.e0 = e0;
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
+    e++;
+  }
+  // end of stream
+  const int slot = e & (TC_NSLOT - 1);
+  TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 3);
+  if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
+}
+
+// ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
+// Eight lanes per token, four tokens per warp-round (fewer, wider instructions per token than a
+// finer split).  What matters besides instruction count is memory-level parallelism (code ->
+// centroid row is a dependent pair of loads, ~1-2k clocks under load), so (a) the eight warps
+// form TC_NTEAMS teams that expand alternate passages concurrently, and (b) a team expands a
+// passage in balanced batches of up to TC_DBATCH rounds with every load of a batch issued
+// before any of it is consumed and the codes of the next batch already requested.  Operand
+// rows past the last token (padding to 16) re-expand the last token: no column masking later.
+template <int NBITS>
+__device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCtx& S, const int team, const int dw, const int warp, const int lane) {
+  Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const ring = S.ring; uint8_t* const s_lut = S.s_lut;
+  (void)warp;
+  const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
+  for (int e = team;; e += TC_NTEAMS) {
+    // An entry of another team between this team's previous entry and e may end the stream.  Every
+    // decompression warp looks at EVERY entry exactly once and is one of the arrivals that release
+    // its meta slot, so the scheduler cannot republish a slot (and flip the parity this probe waits
+    // on) before the probe has happened.
+    bool stop = false;
+    for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
+      const int sl = ee & (TC_NSLOT - 1);
+      TCW(&bar->meta_full[sl], (ee >> TC_NSLOT_LOG2) & 1, 12, 20);
+      if (meta[sl].ncand < 0) { stop = true; break; }
+      if (ee != e) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[sl]); }
+    }
+    if (stop) break;
+    const int slot = e & (TC_NSLOT - 1);
+    const Meta& m = meta[slot];
+    { TCP_BEGIN();
+    if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.nchunk, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
+    TCP_END(20); }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
   }
 }
 
@@ -330,6 +593,10 @@ k_maxsim_tc(TcParams P) {
   // and everything derived from `warp` then stays on the uniform datapath (no WARPSYNC before the
   // TMEM loads, no divergence checks before the reductions: worth ~10 % of kernel time, measured)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+#if TC_PROF
+  for (int i = tid; i < 32 * 24; i += TC_THREADS) s_prof[i] = 0;
+  const long long prof_t0 = clock64();
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
@@ -350,144 +617,20 @@ k_maxsim_tc(TcParams P) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const TcCtx S{ring, a_tile0, meta, bar, s_region, s_lut, NA};
 
   // ===== query-tile loaders: EVERY loader serves EVERY group, loader li fetching the group's queries
   // j = li, li + TC_NLOAD, ...  One warp sustains only ~31 B/clk of 8 KB bulk copies (a copy occupies
   // its issuing warp for ~270 clocks: tools/l2_to_sm_ceiling.cu, profiles/r02_l2_to_sm_ceiling.txt),
   // while the L2 -> SM path itself carries 76 B/clk/SM; spreading one group's four copies over
   // several issuers shortens the fill time of a stage, which is what paces the 3-stage ring. =====
-  auto loader_role = [&](const int li) {
-    uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
-    for (int e = 0;; e++) {
-      const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 8);
-      const Meta& m = meta[slot];
-      const int ncand = m.ncand;
-      if (ncand < 0) break;
-      const int ngroups = (ncand + 3) >> 2;
-      for (int g = 0; g < ngroups; g++) {
-        const uint32_t st_g = st, par_g = a_par;
-        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
-        ptx::mbar_wait(&bar->a_empty[st_g], par_g, 9);
-        const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
-        uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
-        const int nmine = (nqg - li + TC_NLOAD - 1) / TC_NLOAD;      // queries li, li + TC_NLOAD, ... < nqg
-        if (nmine <= 0) {
-          if (ptx::elect_one()) ptx::mbar_arrive(&bar->a_full[st_g]);
-          continue;
-        }
-        const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * TC_NLOAD] : 0;   // lane i holds this loader's i-th query
-        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nmine * TC_Q_BYTES);
-        for (int i = 0; i < nmine; i++) {
-          const int q = __shfl_sync(0xffffffffu, qv, i);
-          if (ptx::elect_one())
-            ptx::bulk_g2s(dst + (li + i * TC_NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
-    }
-  };
 
   // Register budget per warpgroup (setmaxnreg sits at the top of each role's branch so ptxas
   // allocates per role): the epilogue keeps two TMEM load batches in flight, the rest need little.
   if (warp < 4) {
-  if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_dec<96>();
+  tc_reg_budget<TC_REG_CTRL>();
   if (warp == 0) {
-    // ===== scheduler: candidate list, ring allocation and meta of every passage with >= 1 candidate =====
-    const int64_t first = blockIdx.x, stride = gridDim.x;
-    uint32_t head = 0;             // next free byte of the ring
-    int e = 0;                     // entry counter
-    int tail = 0;                  // entries < tail are known to have released their tile
-    // Everything the scheduler reads from global memory for passage p -- its extent, its bitmap words
-    // and the extent of the passage whose packed bytes it will prefetch -- is requested TWO
-    // iterations ahead and carried in registers, so no global latency sits on the per-passage path
-    // (one exposed L2/HBM round trip per passage made the scheduler the bottleneck of the kernel at
-    // ~17 candidates per passage: nothing downstream ever saw a full pipeline).
-    struct Hdr { int64_t o0, o1, f0, f1, p; uint32_t w; };
-    // With a passage list (sparse bitmap) item i is passage pid_list[i]: the pid is requested one more
-    // iteration ahead than the header that depends on it.  (No packed-byte prefetch in that mode.)
-    const int64_t n_items = P.pid_list ? P.n_list : P.Np;
-    auto pid_of = [&](int64_t i) -> int64_t { return (P.pid_list && i < n_items) ? (int64_t)P.pid_list[i] : i; };
-    auto load_hdr = [&](int64_t i, int64_t p) {
-      Hdr h; h.o0 = h.o1 = h.f0 = h.f1 = 0; h.w = 0u; h.p = p;
-      if (i < n_items) {
-        h.o0 = P.offsets[p]; h.o1 = P.offsets[p + 1];
-        h.w = (lane < P.W) ? P.bitmap[p * P.W + lane] : 0u;
-        const int64_t pf = p + 6 * stride;       // pull its packed bytes from HBM into L2 a few passages ahead
-        if (!P.pid_list && pf < P.Np) { h.f0 = P.offsets[pf]; h.f1 = P.offsets[pf + 1]; }
-      }
-      return h;
-    };
-    Hdr h1 = load_hdr(first, pid_of(first)), h2 = load_hdr(first + stride, pid_of(first + stride));
-    int64_t pq = pid_of(first + 2 * stride);
-    for (int64_t it = first; it < n_items; it += stride) {
-      const Hdr h = h1;
-      h1 = h2;
-      const int64_t pq_next = pid_of(it + 3 * stride);
-      h2 = load_hdr(it + 2 * stride, pq);
-      pq = pq_next;
-      const int64_t p = h.p;
-      const int64_t e0 = h.o0;
-      const int L = (int)(h.o1 - h.o0);
-      uint32_t w = h.w;
-      if (h.f1 > h.f0) {
-        const char* r0 = reinterpret_cast<const char*>(P.residuals) + h.f0 * P.R;
-        const char* c0 = reinterpret_cast<const char*>(P.codes) + h.f0 * 4;
-        const int64_t rbytes = (h.f1 - h.f0) * P.R, cbytes = (h.f1 - h.f0) * 4;
-        for (int64_t o = (int64_t)lane * 128; o < rbytes; o += 32 * 128) ptx::prefetch_l2(r0 + o);
-        for (int64_t o = (int64_t)lane * 128; o < cbytes; o += 32 * 128) ptx::prefetch_l2(c0 + o);
-      }
-      if (L <= 0 || L > P.long_limit) w = 0u;          // empty, or too long: the generic kernel scores it
-      if (!__any_sync(0xffffffffu, w != 0u)) continue;  // no query of the batch wants this passage
-      // tile geometry
-      int nchunk, n0, n1;
-      tc_tile_geometry(L, nchunk, n0, n1);
-      const uint32_t bytes = (uint32_t)(n0 + n1) * 256u;
-      // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
-      const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
-      if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
-      // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps.  The
-      // regions of the last TC_NSLOT entries sit in shared memory (dynamically indexed local arrays
-      // would live in local memory, and with the whole carve-out given to shared memory there is no
-      // L1 to hold them)
-      uint32_t off = head;
-      if (off + bytes > (uint32_t)P.ring_bytes) off = 0;
-      int need = tail;             // entries < need must be free
-#pragma unroll
-      for (int j = 1; j < TC_NSLOT; j++) {
-        const int ej = e - j;
-        if (ej >= tail) {
-          const int sj = ej & (TC_NSLOT - 1);
-          if (off < s_region[2 * sj + 1] && s_region[2 * sj] < off + bytes && need < ej + 1) need = ej + 1;
-        }
-      }
-      for (; tail < need; tail++) ptx::mbar_wait(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> TC_NSLOT_LOG2) & 1, 2);
-      __syncwarp();
-      if (lane == 0) { s_region[2 * slot] = off; s_region[2 * slot + 1] = off + bytes; }
-      __syncwarp();
-      head = off + bytes;
-      // candidate list
-      Meta& m = meta[slot];
-      const int c = __popc(w);
-      int pre = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-      int base = pre - c;
-      while (w) { const int b = __ffs(w) - 1; w &= w - 1; m.q[base++] = (uint16_t)(lane * 32 + b); }
-      const int ncand = __shfl_sync(0xffffffffu, pre, 31);
-      if (lane == 0) {
-        m.ncand = ncand; m.L = L; m.nchunk = nchunk; m.n0 = n0; m.n1 = n1; m.pid = (int)p; m.b_off = off; m.e0 = e0;
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
-      e++;
-    }
-    // end of stream
-    const int slot = e & (TC_NSLOT - 1);
-    ptx::mbar_wait(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 3);
-    if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
+    tc_scheduler_role(P, S, warp, lane);
   } else if (warp == 1) {
     // ===== MMA issuer: ONE elected thread runs the whole loop (no per-group elect / reconvergence);
     // stage and parity counters are carried incrementally and every descriptor is a precomputed low
@@ -501,10 +644,11 @@ k_maxsim_tc(TcParams P) {
       uint32_t st = 0, a_par = 0;        // query-tile stage / parity of its next a_full phase
       uint32_t ds = 0, d_par = 1;        // accumulator / parity of its next d_empty phase
       uint32_t eset = 0;                 // epilogue set that consumes the next group
+      [[maybe_unused]] int gc = 0;       // running group count (TC_PROF trace)
       for (int e = 0;; e++) {
         const int slot = e & (TC_NSLOT - 1);
         const uint32_t ph = (e >> TC_NSLOT_LOG2) & 1;
-        ptx::mbar_wait(&bar->meta_full[slot], ph, 4);
+        TCW(&bar->meta_full[slot], ph, 4);
         const int ncand = meta[slot].ncand;
         if (ncand < 0) break;
         const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
@@ -513,20 +657,23 @@ k_maxsim_tc(TcParams P) {
         const uint32_t kb0 = (uint32_t)n0 * 8u, kb1 = (uint32_t)n1 * 8u;   // K-block stride (rows * 128 B) >> 4
         const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
         const int ngroups = (ncand + 3) >> 2;
-        ptx::mbar_wait(&bar->b_full[slot], ph, 5);
+        TCW(&bar->b_full[slot], ph, 5);
         for (int g = 0; g < ngroups; g++) {
 #if TC_TMEM_A
-          ptx::mbar_wait(&bar->at_full[st], a_par, 6);                    // (st / a_par run over the TC_NTA tensor-memory stages here)
+          TCW(&bar->at_full[st], a_par, 6);                    // (st / a_par run over the TC_NTA tensor-memory stages here)
           const uint32_t a_tmem = tmem_base + TC_A_COL0 + st * TC_A_TCOLS;
 #else
-          ptx::mbar_wait(&bar->a_full[st], a_par, 6);
+          TCW(&bar->a_full[st], a_par, 6);
           const uint32_t a_lo = a_lo0 + st * (uint32_t)(TC_A_BYTES >> 4);
 #endif
+          TCT(0, gc);
           for (int c = 0; c < nchunk; c++) {
-            ptx::mbar_wait(&bar->d_empty[ds], d_par, 7);
+            TCW(&bar->d_empty[ds], d_par, 7);
             ptx::tc_fence_after();
+            TCT(1, gc);
             const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
             const uint32_t b_lo = c ? b_lo1 : b_lo0, kb = c ? kb1 : kb0, idesc = c ? idesc1 : idesc0;
+            TCP_BEGIN();
 #pragma unroll
             for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
               const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
@@ -543,21 +690,24 @@ k_maxsim_tc(TcParams P) {
             if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st]);
 #endif
             ptx::tc_commit(&bar->d_full[eset][ds]);
+            TCP_END(16);
+            TCT(2, gc);
             ds ^= 1u;
             d_par ^= (ds == 0u) ? 1u : 0u;
           }
           if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
           if (++st == (uint32_t)(TC_TMEM_A ? TC_NTA : NA)) { st = 0; a_par ^= 1u; }
+          gc++;
         }
         ptx::tc_commit(&bar->b_empty[slot]);   // arrives after the passage's last MMA retires
       }
     }
     __syncwarp();
   } else {
-    loader_role(warp - 2);
+    tc_loader_role<TC_NLOAD>(P, S, warp - 2, warp, lane);
   }
   } else if (warp < TC_DEC_WARP0) {
-    if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_inc<176>();
+    tc_reg_budget<TC_REG_EPI>();
     // ===== epilogue: TMEM -> max over tokens -> sum over query tokens -> pair list =====
     const int q4 = warp & 3;                // TMEM lane quarter == query slot inside the group
     const uint32_t myset = (uint32_t)(warp - 4) >> 2;   // this warp's set scores groups ug % TC_EPI_SETS == myset
@@ -569,6 +719,7 @@ k_maxsim_tc(TcParams P) {
     // atomics in flight at once, and the stores that depend on the atomics' results are deferred
     // to the next flush (software pipelining), so no global latency sits on the per-group path.
     int cnt = 0, my_q = 0;
+    [[maybe_unused]] int gc = 0;
     uint64_t my_key = 0;
     bool pend = false;
     uint64_t pend_key = 0;
@@ -586,7 +737,7 @@ k_maxsim_tc(TcParams P) {
     };
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 10);
+      TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 10);
       const Meta& m = meta[slot];
       const int ncand = m.ncand;
       if (ncand < 0) break;
@@ -596,20 +747,48 @@ k_maxsim_tc(TcParams P) {
       for (int g = 0; g < ngroups; g++) {
         const bool mine = (eset == myset);
         if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
-        if (!mine) { ud += nchunk; continue; }
+        if (!mine) { ud += nchunk; gc++; continue; }
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 chains: ILP for the ALU pipe
         for (int c = 0; c < nchunk; c++, ud++) {
           const int ds = ud & 1;
           const int ncol = (TC_ABLATE & 2) ? 16 : (c ? n1 : n0);
           const int nfull = ncol >> 5;           // full 32-column chunks (<= 7)
-          ptx::mbar_wait(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11);
+          TCW(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11);
           fpar ^= 1u << ds;
           ptx::tc_fence_after();
+          if (warp == 4 || warp == 8) TCT(3, gc);
           const uint32_t taddr = tmem_base + ds * TC_D_COLS + lane_off;
           // max over the chunk's tokens == max over this thread's ncol TMEM columns; the load of
           // the next 32 columns is in flight while the current 32 are folded
           uint32_t ra[32], rt[16];
-          if constexpr (TC_EPI_SETS > 1 || TC_TMEM_A) {
+          if constexpr (TC_EPI_MODE == 2) {
+            // Every load of a step (two 32-column loads + the 16-column tail: 80 columns, the typical passage) is issued
+            // before the ONE tcgen05.wait::ld that covers them (a wait costs > 100 clocks whatever it waits for); once the
+            // last step's values are in registers the accumulator goes back to the MMA issuer, and only then are they folded.
+            uint32_t rb[32];
+            int col = 0;
+            while (true) {
+              const int rem = ncol - col;
+              const int n32 = min(rem >> 5, 2);
+              const bool t16 = (rem - n32 * 32) == 16;
+              if (n32 > 0) ptx::tmem_ld_32x32b_x32(taddr + col, ra);
+              if (n32 > 1) ptx::tmem_ld_32x32b_x32(taddr + col + 32, rb);
+              if (t16) ptx::tmem_ld_32x32b_x16(taddr + col + n32 * 32, rt);
+              ptx::tmem_ld_wait();
+              col += n32 * 32 + (t16 ? 16 : 0);
+              const bool last = col >= ncol;
+              if (last) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bar->d_empty[ds]);
+              }
+              if (n32 > 0) fold32(ra, m0, m1, m2, m3);
+              if (n32 > 1) fold32(rb, m0, m1, m2, m3);
+              if (t16) fold16(rt, m0, m1, m2, m3);
+              if (last) break;
+            }
+          } else {
+          if constexpr (TC_EPI_MODE == 0) {
             // two sets share the work: single-buffered loads keep a set inside the 96 registers every
             // warp of the 640-thread CTA gets (no setmaxnreg: the pool is only what the launch allocated)
 #pragma unroll 1
@@ -641,7 +820,9 @@ k_maxsim_tc(TcParams P) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&bar->d_empty[ds]);
           if (ncol & 16) fold16(rt, m0, m1, m2, m3);
+          }
         }
+        if (warp == 4 || warp == 8) TCT(4, gc);
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         // sum over the 32 query tokens: exact (order-free) integer warp reduction of 2^-18 fixed point.
         // Range: the operand rows are unit vectors, so |mx| <= |q token|; the 32-term sum cannot
@@ -658,6 +839,8 @@ k_maxsim_tc(TcParams P) {
           }
           if (++cnt == 32) flush();
         }
+        if (warp == 4 || warp == 8) TCT(5, gc);
+        gc++;
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
@@ -674,6 +857,7 @@ k_maxsim_tc(TcParams P) {
     // row, which it reads out of the SWIZZLE_128B stage with sixteen conflict-free 16-byte loads (the 8 lanes
     // of a quarter-warp sit on 8 different 16-byte bank groups by construction of the swizzle) and writes as
     // the 64 packed columns of its lane with tcgen05.st. =====
+    tc_reg_budget<TC_REG_CONV>();
     const int j = warp - TC_CONV_WARP0;
     const uint32_t a_lane = tmem_base + TC_A_COL0 + ((uint32_t)(j * 32) << 16);
     // row `lane` of query j inside a stage: 8-row group lane >> 3 (2048 B apart), row lane & 7 (128 B), K-block 1024 B apart
@@ -681,16 +865,19 @@ k_maxsim_tc(TcParams P) {
     const uint32_t r7 = (uint32_t)lane & 7u;
     uint32_t st = 0, a_par = 0;      // shared-memory stage / parity of its next a_full phase
     uint32_t ts = 0, t_par = 1;      // tensor-memory stage / parity of its next at_empty phase
+    [[maybe_unused]] int gc = 0;
     for (int e = 0;; e++) {
       const int slot = e & (TC_NSLOT - 1);
-      ptx::mbar_wait(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 13);
+      TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 13);
       const int ncand = meta[slot].ncand;
       if (ncand < 0) break;
       const int ngroups = (ncand + 3) >> 2;
       for (int g = 0; g < ngroups; g++) {
         const bool have = (TC_ABLATE & 1) ? (j == 0) : (g * 4 + j < ncand);   // a short last group leaves the other quarters stale (never read out)
-        ptx::mbar_wait(&bar->a_full[st], a_par, 14);
+        TCW(&bar->a_full[st], a_par, 14);
+        if (j == 0) TCT(7, gc);
         uint32_t r[64];
+        TCP_BEGIN();
         if (have) {
           const uint8_t* src = a_tile0 + (size_t)st * TC_A_BYTES + row_off;
 #pragma unroll
@@ -699,8 +886,9 @@ k_maxsim_tc(TcParams P) {
             r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
           }
         }
-        ptx::mbar_wait(&bar->at_empty[ts], t_par, 15);
+        TCW(&bar->at_empty[ts], t_par, 15);
         ptx::tc_fence_after();
+        if (j == 0) TCT(8, gc);
         if (have) {
           ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS, r);
           ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS + 32, r + 32);
@@ -711,6 +899,9 @@ k_maxsim_tc(TcParams P) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar->at_full[ts]);
+        TCP_END(18);
+        if (j == 0) TCT(9, gc);
+        gc++;
         if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
         if (++ts == (uint32_t)TC_NTA) { ts = 0; t_par ^= 1u; }
       }
@@ -718,9 +909,9 @@ k_maxsim_tc(TcParams P) {
       if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
     }
   } else {
-    if constexpr (TC_EPI_SETS == 1 && !TC_TMEM_A) ptx::reg_dec<112>();
+    tc_reg_budget<TC_REG_DEC>();
     if (warp < TC_DEC_FIRST) {
-      loader_role(warp - TC_DEC_WARP0 + 2);
+      tc_loader_role<TC_NLOAD>(P, S, warp - TC_DEC_WARP0 + 2, warp, lane);
     } else {
     // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
     // Eight lanes per token, four tokens per warp-round (fewer, wider instructions per token than a
@@ -730,39 +921,432 @@ k_maxsim_tc(TcParams P) {
     // passage in balanced batches of up to TC_DBATCH rounds with every load of a batch issued
     // before any of it is consumed and the codes of the next batch already requested.  Operand
     // rows past the last token (padding to 16) re-expand the last token: no column masking later.
-    const int team = (warp - TC_DEC_FIRST) / TC_TEAM_WARPS, dw = (warp - TC_DEC_FIRST) % TC_TEAM_WARPS;
-    const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
-    for (int e = team;; e += TC_NTEAMS) {
-      // An entry of another team between this team's previous entry and e may end the stream.  Every
-      // decompression warp looks at EVERY entry exactly once and is one of the arrivals that release
-      // its meta slot, so the scheduler cannot republish a slot (and flip the parity this probe waits
-      // on) before the probe has happened.
-      bool stop = false;
-      for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
-        const int sl = ee & (TC_NSLOT - 1);
-        ptx::mbar_wait(&bar->meta_full[sl], (ee >> TC_NSLOT_LOG2) & 1, 12, 20);
-        if (meta[sl].ncand < 0) { stop = true; break; }
-        if (ee != e) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[sl]); }
-      }
-      if (stop) break;
-      const int slot = e & (TC_NSLOT - 1);
-      const Meta& m = meta[slot];
-      if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
-    }
+    tc_decompress_role<NBITS>(P, S, (warp - TC_DEC_FIRST) / TC_TEAM_WARPS, (warp - TC_DEC_FIRST) % TC_TEAM_WARPS, warp, lane);
     }
   }
 
+#if TC_PROF
+  if (lane == 0) s_prof[warp * 24] = (unsigned long long)(clock64() - prof_t0);
+#endif
   ptx::tc_fence_before();
   __syncthreads();
+#if TC_PROF
+  for (int i = tid; i < 32 * 24; i += TC_THREADS) g_tc_prof[(size_t)blockIdx.x * 32 * 24 + i] = s_prof[i];
+#endif
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
+
+// =============================================================================================
+// Two-lane scoring kernel (TC_LANES == 2).
+//
+// Why: the event trace of the one-lane kernel (tools/tc_trace.py, profiles/r02_wait_profile.txt) shows a group's life fully
+// serialised behind ONE thread: the MMA issuer needs ~850 clocks of its own instruction latency per 4-query group (two mbarrier
+// probes, ~50 uniform-datapath instructions of descriptor arithmetic, 8 tcgen05.mma + 2 commits) whatever the tensor pipe is
+// doing; the shared-memory-operand MMAs of a group occupy the tensor pipe for (4 KB A + 2.5 KB B) / 64 B/clk x 8 = ~830 clocks; and
+// one epilogue set needs ~750.  Three unrelated ~800-clock limits in a row: removing any one of them (two issuers; A in tensor
+// memory; two epilogue sets) alone changes nothing, which is what eleven A/B builds had measured.  This kernel removes all three:
+//   * groups alternate between two LANES; lane s = issuer warp s + worker set s (4 warps) + accumulator s + A-tile s in tensor memory;
+//   * the A operand is read from TENSOR MEMORY (tcgen05.mma [tmem], desc_b): a group's 8 MMAs take 8 x N/2 clocks of pure math;
+//   * a WORKER warp (one per TMEM lane quarter = one query of the group) is converter and epilogue in one: when the lane's MMAs
+//     retire it stores the NEXT group's query rows (already waiting in its registers) into the A tile with tcgen05.st, reads the
+//     accumulator (max over tokens), hands both back to the issuer with ONE barrier arrival, then sums / records the score and
+//     pulls the rows of the group after next out of the bulk-copy stage (conflict-free LDS of the swizzled tile).
+// Everything else (scheduler, loaders, decompression teams, pair-list output) is shared with k_maxsim_tc.
+//   * TWO A tiles per lane: the rows of the lane's group i+2 are stored (off the critical path, right after they were pulled out
+//     of the bulk-copy stage) into the tile group i used, whose MMAs have retired, while group i+1's MMAs run out of the other.
+// Tensor memory: lane s owns columns 256 s .. 256 s + 255: accumulator (128 columns: N <= 128 per chunk, up to 3 chunks per
+// passage) at +0, A tiles (64 packed columns each) at +128 and +192.
+// =============================================================================================
+constexpr int T2_NLOAD = 4;                         // loader warps 4..7
+constexpr int T2_WORK_WARP0 = 8, T2_DEC_WARP0 = 16; // workers 8..15 (set = (warp - 8) >> 2), decompression 16..23
+constexpr int T2_THREADS = 32 * 24;
+constexpr uint32_t T2_LANE_COLS = 256, T2_A_COL0 = 128, T2_A_TCOLS = 64;
+#ifndef T2_READ_MODE
+#define T2_READ_MODE 0
+#endif
+#ifndef T2_REG_CTRL
+#define T2_REG_CTRL 48
+#define T2_REG_LOAD 32
+#define T2_REG_WORK 104
+#define T2_REG_DEC 96
+#endif
+template <int N> __device__ __forceinline__ void t2_reg_budget() {   // 768 threads: launch allocation 80
+  if constexpr (N > 80) ptx::reg_inc<N>();
+  else if constexpr (N > 0 && N < 80) ptx::reg_dec<N>();
+}
+
+// Position in the CTA's stream of groups: passage entry e, group g of its ng, global group index G (lane = G & 1) and the
+// bulk-copy stage / phase parity of group G.  `pending`: entry e has not been read yet (it may not be published yet).
+struct T2Cursor {
+  int e, g, ng, ncand; uint32_t G, st, q, par; bool pending, end;   // q = G % period, par = (G / period) & 1 (period: t2_loader_role)
+};
+
+// Query-tile loaders of the two-lane kernel.  Group G lands in stage G % NA as in k_maxsim_tc, but its full / empty barriers are
+// the ones of its LANE (G & 1): a barrier phase must be observed by every party that waits on the barrier, in order -- a lane's
+// workers never look at the other lane's groups, and with one barrier per stage a worker asking for group G while the stage
+// still waits for group G - NA (the other lane's) would see the phase of G - 2 NA, same parity, as complete.  Barrier
+// (lane, stage) serves every `period`-th group, period = lcm(2, NA): phase of group G = G / period.
+template <int NLOAD>
+__device__ __forceinline__ void t2_loader_role(const TcParams& P, const TcCtx& S, const int li, const int warp, const int lane) {
+  Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const a_tile0 = S.a_tile0;
+  const uint32_t NA = (uint32_t)S.NA, period = (NA & 1u) ? 2u * NA : NA;
+  (void)warp;
+  uint32_t G = 0, st = 0;        // group counter / its stage
+  uint32_t pq = 0, pph = 0;      // (G - NA) % period and the phase parity of group G - NA, the stage's previous user
+  for (int e = 0;; e++) {
+    const int slot = e & (TC_NSLOT - 1);
+    TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 8);
+    const Meta& m = meta[slot];
+    const int ncand = m.ncand;
+    if (ncand < 0) break;
+    const int ngroups = (ncand + 3) >> 2;
+    for (int g = 0; g < ngroups; g++) {
+      if (G >= NA) {
+        TCW(&bar->t2_aempty[(G - NA) & 1u][st], pph, 9);
+        if (++pq == period) { pq = 0; pph ^= 1u; }
+      }
+      if (li == 0) TCT(6, (int)G);
+      uint64_t* const full = &bar->t2_afull[G & 1u][st];
+      uint8_t* dst = a_tile0 + (size_t)st * TC_A_BYTES;
+      G++;
+      if (++st == NA) st = 0;
+      const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
+      const int nmine = (nqg - li + NLOAD - 1) / NLOAD;      // queries li, li + NLOAD, ... < nqg
+      if (nmine <= 0) {
+        if (ptx::elect_one()) ptx::mbar_arrive(full);
+        continue;
+      }
+      const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * NLOAD] : 0;   // lane i holds this loader's i-th query
+      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full, (uint32_t)nmine * TC_Q_BYTES);
+      for (int i = 0; i < nmine; i++) {
+        const int q = __shfl_sync(0xffffffffu, qv, i);
+        if (ptx::elect_one())
+          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
+  }
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+k_maxsim_tc2(TcParams P) {
+  if (*P.q_flag != 0) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NA = P.nastages;
+  uint8_t* ring = smem;
+  uint8_t* a_tile0 = smem + P.ring_bytes;
+  Meta* meta = reinterpret_cast<Meta*>(a_tile0 + (size_t)NA * TC_A_BYTES);
+  Barriers* bar = reinterpret_cast<Barriers*>(meta + TC_NSLOT);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* s_region = s_tmem + 4;
+  uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_region + 2 * TC_NSLOT) + 64;
+  s_lut += (128u - (ptx::smem_u32(s_lut) & 127u)) & 127u;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+#if TC_PROF
+  for (int i = tid; i < 32 * 24; i += T2_THREADS) s_prof[i] = 0;
+  const long long prof_t0 = clock64();
+#endif
+  if (tid == 0) {
+    for (int i = 0; i < TC_NSLOT; i++) {
+      ptx::mbar_init(&bar->b_full[i], TC_TEAM_WARPS); ptx::mbar_init(&bar->b_empty[i], 2);          // both issuers commit
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], T2_NLOAD + 8 + TC_NDEC_WARPS + 2);
+    }
+    for (int i = 0; i < 2 * TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->t2_afull[0][i], T2_NLOAD); ptx::mbar_init(&bar->t2_aempty[0][i], 4); }
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(&bar->l_afull[i][0], 4); ptx::mbar_init(&bar->l_afull[i][1], 4);
+      ptx::mbar_init(&bar->l_dempty[i], 4);   ptx::mbar_init(&bar->l_dfull[i], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  tc_fill_lut<NBITS>(s_lut, P.weights, tid, T2_THREADS);
+  if (warp == 1) ptx::tmem_alloc(s_tmem, TC_TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const TcCtx S{ring, a_tile0, meta, bar, s_region, s_lut, NA};
+  const uint32_t period = (NA & 1) ? 2u * (uint32_t)NA : (uint32_t)NA;   // groups between two uses of a (lane, stage) barrier
+
+  // Cursor over the stream of groups.  cur_seek(c, s, blocking, release) moves c to the next group of lane s at or after its
+  // position (or to the end of the stream); with blocking = false it gives up -- returns false, resumable -- as soon as it would
+  // need a passage entry the scheduler has not published yet.  cur_skip steps past the group c is on.  `release`: this walker is
+  // one of the arrivals that free a passage's meta slot when it leaves the passage.
+  // non-blocking probe of a barrier phase with ONE answer for the whole warp: the lanes of a warp can see a phase complete at
+  // different instants, and a warp split on the answer would run .sync.aligned tensor-memory instructions with a partial mask
+  auto probe = [&](uint64_t* b, uint32_t parity) __attribute__((always_inline)) -> bool {
+    return __shfl_sync(0xffffffffu, ptx::mbar_test_wait(b, parity) ? 1 : 0, 0) != 0;
+  };
+  auto cur_start = [&](T2Cursor& c) __attribute__((always_inline)) {
+    c.e = 0; c.g = 0; c.ng = 0; c.ncand = 0; c.G = 0; c.st = 0; c.q = 0; c.par = 0; c.pending = true; c.end = false;
+  };
+  auto cur_skip = [&](T2Cursor& c, bool release) __attribute__((always_inline)) {
+    c.G++;
+    if (++c.st == (uint32_t)NA) c.st = 0;
+    if (++c.q == period) { c.q = 0; c.par ^= 1u; }
+    if (++c.g < c.ng) return;
+    if (release) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[c.e & (TC_NSLOT - 1)]); }
+    c.e++;
+    c.pending = true;
+  };
+  auto cur_seek = [&](T2Cursor& c, uint32_t s, bool blocking, bool release, int tag) __attribute__((always_inline)) -> bool {
+    while (true) {
+      if (c.pending) {
+        const int slot = c.e & (TC_NSLOT - 1);
+        const uint32_t ph = (c.e >> TC_NSLOT_LOG2) & 1;
+        if (blocking) TCW(&bar->meta_full[slot], ph, tag);
+        else if (!probe(&bar->meta_full[slot], ph)) return false;
+        c.ncand = meta[slot].ncand;
+        c.end = c.ncand < 0;
+        c.ng = (c.ncand + 3) >> 2;
+        c.g = 0;
+        c.pending = false;
+      }
+      if (c.end || (c.G & 1u) == s) return true;
+      cur_skip(c, release);
+    }
+  };
+
+  if (warp < 4) {
+    t2_reg_budget<T2_REG_CTRL>();
+    if (warp == 0) {
+      tc_scheduler_role(P, S, warp, lane);
+    } else if (warp <= 2) {
+      // ===== MMA issuer of lane s: ONE elected thread; walks every passage (it is one of the arrivals that free the passage's
+      // operand tile and meta slot) and issues the groups with G & 1 == s =====
+      const uint32_t s = (uint32_t)(warp - 1);
+      if (ptx::elect_one()) {
+        const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);
+        constexpr uint32_t HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t d_tmem = tmem_base + s * T2_LANE_COLS, a_tmem0 = d_tmem + T2_A_COL0;
+        uint32_t dpar = 1;                 // parity of the lane's next l_dempty phase (the accumulator starts out free)
+        uint32_t own = 0;                  // own groups issued: A tile = own & 1, phase parity of its l_afull = (own >> 1) & 1
+        [[maybe_unused]] int gc = 0;
+        T2Cursor c;
+        cur_start(c);
+        int e_cur = -1;
+        int nchunk = 1, n0 = 16, n1 = 0;
+        uint32_t b_lo0 = 0, kb0 = 0, kb1 = 0, idesc0 = 0, idesc1 = 0;
+        while (true) {
+          // every group of the stream, in order (blocking); a passage is left -- b_empty / meta_empty -- when its last group is passed
+          if (c.pending) {
+            const int slot = c.e & (TC_NSLOT - 1);
+            TCW(&bar->meta_full[slot], (c.e >> TC_NSLOT_LOG2) & 1, 4);
+            c.ncand = meta[slot].ncand;
+            c.end = c.ncand < 0;
+            c.ng = (c.ncand + 3) >> 2;
+            c.g = 0;
+            c.pending = false;
+          }
+          if (c.end) break;
+          const int slot = c.e & (TC_NSLOT - 1);
+          if ((c.G & 1u) == s) {
+            if (e_cur != c.e) {              // first own group in this passage: its geometry, and its operand tile must be complete
+              e_cur = c.e;
+              nchunk = meta[slot].nchunk; n0 = meta[slot].n0; n1 = meta[slot].n1;
+              b_lo0 = ring_lo + (meta[slot].b_off >> 4);
+              kb0 = (uint32_t)n0 * 8u; kb1 = (uint32_t)n1 * 8u;
+              idesc0 = ptx::idesc_f16(128, n0, 0); idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
+              TCW(&bar->b_full[slot], (c.e >> TC_NSLOT_LOG2) & 1, 5);
+            }
+            const uint32_t tile = own & 1u;
+            TCW(&bar->l_afull[s][tile], (own >> 1) & 1u, 6);
+            TCT(0, gc);
+            own++;
+            const uint32_t a_tmem = a_tmem0 + tile * T2_A_TCOLS;
+            for (int ch = 0; ch < nchunk; ch++) {
+              TCW(&bar->l_dempty[s], dpar, 7);
+              dpar ^= 1u;
+              ptx::tc_fence_after();
+              TCT(1, gc);
+              const bool lastc = (nchunk > 1) && (ch == nchunk - 1);
+              const uint32_t b_lo = b_lo0 + (uint32_t)(ch * n0) * 16u, kb = lastc ? kb1 : kb0, idesc = lastc ? idesc1 : idesc0;
+              TCP_BEGIN();
+#pragma unroll
+              for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
+                const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
+                ptx::mma_f16_ts(d_tmem, a_tmem + (uint32_t)k * 8u, db, idesc, k > 0 ? 1u : 0u);
+              }
+              ptx::tc_commit(&bar->l_dfull[s]);
+              TCP_END(16);
+              TCT(2, gc);
+            }
+            gc++;
+          }
+          // leaving the passage: this issuer's MMAs on its tile have been issued -> b_empty arrives when they retire
+          if (c.g + 1 >= c.ng) { ptx::tc_commit(&bar->b_empty[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
+          cur_skip(c, false);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp < T2_WORK_WARP0) {
+    t2_reg_budget<T2_REG_LOAD>();
+    t2_loader_role<T2_NLOAD>(P, S, warp - 4, warp, lane);
+  } else if (warp < T2_DEC_WARP0) {
+    t2_reg_budget<T2_REG_WORK>();
+    // ===== worker of lane s, TMEM lane quarter q4 (= query slot q4 of every group of the lane) =====
+    const int q4 = warp & 3;
+    const uint32_t s = (uint32_t)(warp - T2_WORK_WARP0) >> 2;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t d_addr = tmem_base + s * T2_LANE_COLS + lane_off, a_addr0 = d_addr + T2_A_COL0;
+    // row `lane` of query q4 inside a bulk-copy stage (converter geometry of k_maxsim_tc)
+    const uint32_t row_off = (uint32_t)q4 * TC_Q_BYTES + (uint32_t)(lane >> 3) * 2048u + (uint32_t)(lane & 7) * 128u;
+    const uint32_t r7 = (uint32_t)lane & 7u;
+    uint32_t dpar = 0;                       // parity of the lane's next l_dfull phase
+    int cnt = 0, my_q = 0;
+    uint64_t my_key = 0;
+    bool pend = false;
+    uint64_t pend_key = 0;
+    uint64_t* pend_ptr = nullptr;
+    int pend_pos = 0;
+    auto flush = [&]() __attribute__((always_inline)) {
+      if (pend) pend_ptr[pend_pos] = pend_key;
+      pend = lane < cnt;
+      if (pend) {
+        pend_ptr = P.pairs + P.list_off[my_q];
+        pend_pos = atomicAdd(&P.cursors[my_q], 1);
+        pend_key = my_key;
+      }
+      cnt = 0;
+    };
+    // Query rows of group `c` : bulk-copy stage -> registers -> A tile `tile` of the lane (all four quarters do it whether or not
+    // the group has a query in their slot: a stale row only produces an accumulator row nobody reads); the stage goes back to the
+    // loaders, the tile is handed to the issuer.
+    auto convert = [&](const T2Cursor& c, uint32_t tile) __attribute__((always_inline)) {
+      uint32_t r[64];                         // this thread's (query, token) row: 128 fp16 = 64 packed columns
+      TCW(&bar->t2_afull[s][c.st], c.par, 14);
+      const uint8_t* src = a_tile0 + (size_t)c.st * TC_A_BYTES + row_off;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (i >> 3) * 1024 + ((((uint32_t)i & 7u) ^ r7) << 4));
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->t2_aempty[s][c.st]);
+      const uint32_t a_addr = a_addr0 + tile * T2_A_TCOLS;
+      ptx::tmem_st_32x32b_x32(a_addr, r);
+      ptx::tmem_st_32x32b_x32(a_addr + 32, r + 32);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->l_afull[s][tile]);
+    };
+    // max over one chunk's accumulator columns
+    auto read_chunk = [&](int ncol, float& m0, float& m1, float& m2, float& m3) __attribute__((always_inline)) {
+#if T2_READ_MODE == 0
+      // one 32-column piece at a time (fewest registers)
+      const int nfull = ncol >> 5;
+      uint32_t ra[32];
+#pragma unroll 1
+      for (int p = 0; p < nfull; p++) {
+        ptx::tmem_ld_32x32b_x32(d_addr + p * 32, ra);
+        ptx::tmem_ld_wait();
+        fold32(ra, m0, m1, m2, m3);
+      }
+      if (ncol & 16) {
+        uint32_t rt[16];
+        ptx::tmem_ld_32x32b_x16(d_addr + nfull * 32, rt);
+        ptx::tmem_ld_wait();
+        fold16(rt, m0, m1, m2, m3);
+      }
+#else
+      // pieces of 32 columns (+ a 16-column tail), the load of the next piece in flight while the current one is folded
+      const int nfull = ncol >> 5, np = nfull + ((ncol >> 4) & 1);
+      uint32_t ra[32], rb[32];
+      if (nfull > 0) ptx::tmem_ld_32x32b_x32(d_addr, ra); else ptx::tmem_ld_32x32b_x16_lo(d_addr, ra);
+      ptx::tmem_ld_wait();
+      for (int p = 0; p < np; p += 2) {
+        if (p + 1 < np) { if (p + 1 < nfull) ptx::tmem_ld_32x32b_x32(d_addr + (p + 1) * 32, rb); else ptx::tmem_ld_32x32b_x16_lo(d_addr + (p + 1) * 32, rb); }
+        if (p < nfull) fold32(ra, m0, m1, m2, m3); else fold16_lo(ra, m0, m1, m2, m3);
+        if (p + 1 >= np) break;
+        ptx::tmem_ld_wait();
+        if (p + 2 < np) { if (p + 2 < nfull) ptx::tmem_ld_32x32b_x32(d_addr + (p + 2) * 32, ra); else ptx::tmem_ld_32x32b_x16_lo(d_addr + (p + 2) * 32, ra); }
+        if (p + 1 < nfull) fold32(rb, m0, m1, m2, m3); else fold16_lo(rb, m0, m1, m2, m3);
+        if (p + 2 < np) ptx::tmem_ld_wait();
+      }
+#endif
+    };
+    // Epilogue cursor ec (blocking; releases passages) and converter cursor cc (the next group to convert; up to two own groups
+    // ahead of ec).  The converter only BLOCKS -- on a passage entry or a query tile -- when the lane has nothing in flight
+    // (conv == done: the group it needs is the one ec stands on, whose passage is already published); otherwise it converts
+    // opportunistically, so a warp never waits for a future passage while it still holds what that passage's ring space
+    // depends on.
+    T2Cursor ec, cc;
+    cur_start(ec);
+    cur_seek(ec, s, true, true, 10);
+    cc = ec;
+    uint32_t conv = 0, done = 0;
+    bool cc_end = false;
+    [[maybe_unused]] int gc = 0;
+    while (!ec.end) {
+      while (conv - done < 2u && !cc_end) {
+        const bool blocking = (conv == done);
+        if (!cur_seek(cc, s, blocking, false, 13)) break;
+        if (cc.end) { cc_end = true; break; }
+        if (!blocking && !probe(&bar->t2_afull[s][cc.st], cc.par)) break;
+        convert(cc, conv & 1u);
+        conv++;
+        cur_skip(cc, false);
+      }
+      const int slot = ec.e & (TC_NSLOT - 1);
+      const Meta& m = meta[slot];
+      const int nchunk = m.nchunk;
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      for (int ch = 0; ch < nchunk; ch++) {
+        TCW(&bar->l_dfull[s], dpar, 11);
+        dpar ^= 1u;
+        ptx::tc_fence_after();
+        if (q4 == 0 && ch == 0) TCT(3, gc);
+        read_chunk((TC_ABLATE & 2) ? 16 : ((nchunk > 1 && ch == nchunk - 1) ? m.n1 : m.n0), m0, m1, m2, m3);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->l_dempty[s]);   // accumulator drained
+      }
+      if (q4 == 0) TCT(4, gc);
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 262144.0f));   // exact 2^-18 fixed-point sum (k_maxsim_tc)
+      const int qi = ec.g * 4 + q4;
+      if (qi < ec.ncand) {
+        const float score = (float)isum * (1.0f / 262144.0f);
+        if (lane == (cnt & 31)) {
+          my_q = m.q[qi];
+          my_key = ((uint64_t)cb_orderable(score) << 32) | (0xffffffffu - (uint32_t)m.pid);
+        }
+        if (++cnt == 32) flush();
+      }
+      if (q4 == 0) TCT(5, gc);
+      gc++;
+      done++;
+      cur_skip(ec, true);
+      cur_seek(ec, s, true, true, 10);
+    }
+    flush();
+    flush();
+  } else {
+    t2_reg_budget<T2_REG_DEC>();
+    tc_decompress_role<NBITS>(P, S, (warp - T2_DEC_WARP0) / TC_TEAM_WARPS, (warp - T2_DEC_WARP0) % TC_TEAM_WARPS, warp, lane);
+  }
+
+#if TC_PROF
+  if (lane == 0) s_prof[warp * 24] = (unsigned long long)(clock64() - prof_t0);
+#endif
+  ptx::tc_fence_before();
+  __syncthreads();
+#if TC_PROF
+  for (int i = tid; i < 32 * 24; i += T2_THREADS) g_tc_prof[(size_t)blockIdx.x * 32 * 24 + i] = s_prof[i];
+#endif
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
 
 // Parity hook (cb_debug_tc_operand): the decompression of the scoring kernel -- the SAME device functions,
 // one team of TC_TEAM_WARPS warps per listed passage -- with the operand tile copied out un-swizzled.
@@ -774,8 +1358,8 @@ k_tc_dump(TcParams P, const int32_t* __restrict__ pids, const int64_t* __restric
           __half* __restrict__ out_raw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* tile0 = smem;                                   // up to 2 * TC_MAX_BROWS + 32 rows
-  uint8_t* s_lut = smem + (2 * TC_MAX_BROWS + 32) * 256;
+  uint8_t* tile0 = smem;                                   // up to TC_MAX_CHUNKS * (TC_MAX_BROWS + 16) rows
+  uint8_t* s_lut = smem + TC_MAX_CHUNKS * (TC_MAX_BROWS + 16) * 256;
   const int tid = threadIdx.x, dw = tid >> 5, lane = tid & 31;
   tc_fill_lut<NBITS>(s_lut, P.weights, tid, 32 * TC_TEAM_WARPS);
   __syncthreads();
@@ -786,13 +1370,13 @@ k_tc_dump(TcParams P, const int32_t* __restrict__ pids, const int64_t* __restric
   int nchunk, n0, n1;
   tc_tile_geometry(L, nchunk, n0, n1);
   const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
-  tc_decompress_passage<NBITS, true>(P, lut_lane, dw, lane, L, n0, n1, e0, tile0, out_raw + out_off[blockIdx.x] * TC_DIM);
+  tc_decompress_passage<NBITS, true>(P, lut_lane, dw, lane, L, nchunk, n0, n1, e0, tile0, out_raw + out_off[blockIdx.x] * TC_DIM);
   __syncthreads();
   // row rr of chunk c, 16-byte chunk j (K-block j >> 3): the inverse of the address finish_token16 wrote
   for (int i = tid; i < L * 16; i += 32 * TC_TEAM_WARPS) {
     const int rr = i >> 4, j = i & 15;
-    const int c = rr >= n0 ? 1 : 0, row = rr - c * n0;
-    const uint8_t* t = (c ? tile0 + n0 * 256 : tile0) + (j >> 3) * ((c ? n1 : n0) * 128);
+    const int c = (rr >= n0 ? 1 : 0) + (rr >= 2 * n0 ? 1 : 0), row = rr - c * n0;
+    const uint8_t* t = tile0 + c * n0 * 256 + (j >> 3) * (((nchunk > 1 && c == nchunk - 1) ? n1 : n0) * 128);
     const uint4 v = *reinterpret_cast<const uint4*>(t + (row >> 3) * 1024 + (row & 7) * 128 + (((j & 7) ^ (row & 7)) << 4));
     *reinterpret_cast<uint4*>(out_norm + (out_off[blockIdx.x] + rr) * TC_DIM + j * 8) = v;
   }
@@ -824,7 +1408,7 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   CB_REQUIRE(cb_stage34_tc_supported(ix, T), CB_ERR_UNSUPPORTED, "shape not supported by the tcgen05 scoring kernel");
   if (nq == 0 || ix->Np == 0) return CB_OK;
   // shared-memory split: query-tile stages vs. the operand-tile ring
-  const size_t budget = 232448;  // 227 KB opt-in shared memory per CTA on sm_100
+  const size_t budget = 232448 - (TC_PROF ? 7168 : 0);  // 227 KB opt-in shared memory per CTA on sm_100 (minus the static counters of a TC_PROF build)
   int nast = ix->opt_tc_astages > 0 ? ix->opt_tc_astages : 3;
   if (nast < 2) nast = 2;
   if (nast > TC_MAX_ASTAGES) nast = TC_MAX_ASTAGES;
@@ -833,9 +1417,9 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
              "internal: tcgen05 kernel shared memory does not fit");
   const size_t ring = (budget - fixed - (size_t)nast * TC_A_BYTES) & ~(size_t)1023;
   // the ring must hold the largest passage the kernel takes; longer ones go to the generic kernel
-  int64_t long_limit = 2 * TC_MAX_BROWS;
+  int64_t long_limit = TC_MAX_CHUNKS * TC_MAX_BROWS;
   {
-    const int64_t ring_rows = (int64_t)(ring / 256) - 32;    // chunk padding: up to 2 x 15 extra rows
+    const int64_t ring_rows = (int64_t)(ring / 256) - 16 * TC_MAX_CHUNKS;    // chunk padding: up to 15 extra rows per chunk
     if (long_limit > ring_rows) long_limit = ring_rows;
     if (long_limit < 1) long_limit = 1;
   }
@@ -860,10 +1444,17 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   int64_t grid = ix->sm_count;
   const int64_t n_items = P.pid_list ? P.n_list : ix->Np;
   if (grid > n_items) grid = n_items;
+#if TC_LANES == 2
+#define CB_TC_KERNEL k_maxsim_tc2
+#define CB_TC_NTHREADS T2_THREADS
+#else
+#define CB_TC_KERNEL k_maxsim_tc
+#define CB_TC_NTHREADS TC_THREADS
+#endif
 #define CB_TC_LAUNCH(NB)                                                                                         \
   do {                                                                                                           \
-    CB_CUDA(cudaFuncSetAttribute(k_maxsim_tc<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_maxsim_tc<NB><<<(unsigned)grid, TC_THREADS, smem, st>>>(P);                                                \
+    CB_CUDA(cudaFuncSetAttribute(CB_TC_KERNEL<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    CB_TC_KERNEL<NB><<<(unsigned)grid, CB_TC_NTHREADS, smem, st>>>(P);                                           \
   } while (0)
   if (ix->nbits == 1) CB_TC_LAUNCH(1);
   else if (ix->nbits == 2) CB_TC_LAUNCH(2);
@@ -891,6 +1482,19 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   }
   return CB_OK;
 }
+
+#if TC_PROF
+extern "C" int32_t cb_debug_tc_prof(unsigned long long* out /* [160][32][24] */) {
+  CB_CUDA(cudaDeviceSynchronize());
+  CB_CUDA(cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 160 * 32 * 24));
+  return CB_OK;
+}
+extern "C" int32_t cb_debug_tc_trace(long long* out /* [12][4096] */) {
+  CB_CUDA(cudaDeviceSynchronize());
+  CB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 12 * TC_TRACE_N));
+  return CB_OK;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // parity hook: what the tcgen05 kernel's decompression writes into its operand tiles
@@ -926,7 +1530,7 @@ extern "C" int32_t cb_debug_tc_operand(cb_index* ix, const int64_t* pids, int64_
   int64_t* off = reinterpret_cast<int64_t*>(&off_h[0]);
   CB_CUDA(cudaMemcpy(lens, d_lens, sizeof(int64_t) * n_pids, cudaMemcpyDeviceToHost));
   int64_t total = 0;
-  const int64_t long_limit = 2 * TC_MAX_BROWS;
+  const int64_t long_limit = TC_MAX_CHUNKS * TC_MAX_BROWS;
   for (int64_t i = 0; i < n_pids; i++) {
     CB_REQUIRE(lens[i] >= 0, CB_ERR_BOUNDS, "pid out of range 1:%lld (+ pid_base)", (long long)ix->Np);
     CB_REQUIRE(lens[i] <= long_limit, CB_ERR_UNSUPPORTED, "passage longer than the tcgen05 kernel takes (%lld tokens)", (long long)lens[i]);
@@ -943,7 +1547,7 @@ extern "C" int32_t cb_debug_tc_operand(cb_index* ix, const int64_t* pids, int64_
   TcParams P{};
   P.centroids_h = ix->centroids_h; P.weights = ix->weights; P.codes = ix->codes; P.residuals = ix->residuals;
   P.offsets = ix->offsets; P.Np = ix->Np; P.R = ix->R; P.long_limit = (int)long_limit;
-  const size_t smem = 1024 + (size_t)(2 * TC_MAX_BROWS + 32) * 256 + TC_LUT_BYTES + 128;
+  const size_t smem = 1024 + (size_t)TC_MAX_CHUNKS * (TC_MAX_BROWS + 16) * 256 + TC_LUT_BYTES + 128;
 #define CB_TC_DUMP(NB)                                                                                          \
   do {                                                                                                          \
     CB_CUDA(cudaFuncSetAttribute(k_tc_dump<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \

@@ -5,7 +5,7 @@ for spec in $SPECS; do
   lib=${spec%%:*}; opts=""
   if [[ "$spec" == *:* ]]; then for kv in $(echo "${spec#*:}" | tr ',' ' '); do opts="$opts --opt $kv"; done; fi
   for wl in ${@:-C B}; do
-    COLBERT_B200_LIB=$PWD/$lib timeout 300 python bench.py --workload $wl --steps 3 --warmup 2 --no-cpu-baseline --no-extra --no-gate $BENCH_EXTRA $opts > gpurun_out/ab.json 2> gpurun_out/ab.err || { tail -3 gpurun_out/ab.err; head -c 600 gpurun_out/ab.json; }
+    COLBERT_B200_LIB=$PWD/$lib timeout ${BENCH_TMO:-120} python bench.py --workload $wl --steps 3 --warmup 2 --no-cpu-baseline --no-extra --no-gate $BENCH_EXTRA $opts > gpurun_out/ab.json 2> gpurun_out/ab.err || { tail -3 gpurun_out/ab.err; head -c 600 gpurun_out/ab.json; }
     python - <<PY
 import json
 try:
