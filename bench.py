@@ -281,6 +281,7 @@ class Leg:
         self.rank, self.world, self.dist = rank, world, dist
         self.dev = torch.device("cuda", local)
         self.local = local
+        self.sm_mhz = None       # SM clock sampled during the timed region (denominator of the shared-memory data-pipe roofline)
         wl = self.wl
         self.cen, self.doclens, self.csum = gen_global(torch, wl, self.dev)
         bounds = shard_bounds(torch, self.csum, world)
@@ -350,6 +351,8 @@ class Leg:
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         clocks = sampler.stop() if sampler else None
+        if clocks and clocks.get("sm_mhz"):
+            self.sm_mhz = float(clocks["sm_mhz"])
         return float(ms.item()) / steps, clocks
 
     def stage_profile(self, nprof=3):
@@ -384,6 +387,24 @@ class Leg:
             if traffic is None and os.path.exists(tpath) and self.world == 1 and not args.force_generic and self.profile == "uniform":
                 traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(f"{workload_key}:nbits={self.nbits}")
         l2_bytes = pairs * 8192.0 + self.ne_local * (256.0 + 4 + R)
+        # Shared-memory data pipe (128 B/clk/SM): what the launch moves through it, from the kernel's own counters of the last
+        # step -- per 4-query group the 32 KB query tile is written once (bulk copy) and read once (the MMA's A operand), the
+        # passage tile (N rows x 256 B) is read once per group (B operand), and every decompressed row costs a 256 B store and
+        # 256 B of bucket-weight table reads.  tools/mma_operand_bench.cu: a shared-memory-operand MMA streams 128 B/clk.
+        try:
+            groups, group_rows, passage_rows = self.s.stat("tc_groups"), self.s.stat("tc_group_rows"), self.s.stat("tc_passage_rows")
+        except Exception:
+            groups = group_rows = passage_rows = 0.0
+        smem_bytes = groups * 65536.0 + group_rows * 256.0 + passage_rows * 512.0
+        sm_hz = (self.sm_mhz or 0.0) * 1e6
+        smem_peak = 128.0 * 148 * sm_hz / 1e9
+        smem = {"bytes_per_launch": smem_bytes, "achieved": smem_bytes / t34 / 1e9 if t34 > 0 else 0.0, "unit": "GB/s",
+                "peak": smem_peak, "frac": (smem_bytes / t34 / 1e9 / smem_peak) if (t34 > 0 and smem_peak > 0) else None,
+                "groups_per_launch": groups, "clocks_per_group_per_sm": (t34 * sm_hz * 148 / groups) if groups else None,
+                "peak_source": "128 B/clk/SM x 148 SMs x the SM clock sampled during the timed region",
+                "note": "the resource that bounds k_maxsim_tc (DESIGN.md section 4): bulk-copy writes + tcgen05 operand reads + "
+                        "decompression stores / table reads share the SM's 128 B/clk shared-memory data pipe; measured in isolation "
+                        "(profiles/r02_mma_operand_bench.txt) an M=128, N=80 shared-memory-operand MMA takes 52 clocks = 128 B/clk"}
         return {"kernel": "k_maxsim_tc (fused decompress + MaxSim, tcgen05)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                 "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": traffic,
                 "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
@@ -397,6 +418,7 @@ class Leg:
                              "note": "8 KB query tile per pair + 292 B per indexed embedding; ceilings measured by "
                                      "tools/l2_to_sm_ceiling.cu (profiles/r02_l2_to_sm_ceiling.txt); the kernel is bound by the "
                                      "shared-memory / L1 data pipe (TMA writes + UMMA operand reads + LSU), DESIGN.md section 4"},
+                "smem_data_pipe": smem,
                 "stage_ms": prof, "pairs_per_step": pairs, "pair_embeddings_per_step": pair_embs}
 
 
@@ -675,7 +697,7 @@ def main():
             t_leg = time.perf_counter()
             try:
                 lg = Leg(torch, cb, args, wk, nb, profile, nprobe, kk, 0, 1, local, None)
-                ms, _ = lg.timed(args.extra_steps, 3, plaid=plaid)
+                ms, _ = lg.timed(args.extra_steps, 3, plaid=plaid, sample_clocks=True)
                 out = {"workload": WORKLOADS[wk]["name"], "nbits": nb, "code_profile": profile, "nprobe": nprobe, "k": kk,
                        "ms_per_step": ms, "value": nq / (ms * 1e-3), "unit": "queries/s", "steps": args.extra_steps, "warmup": 3,
                        "digest": digest(lg.out_p, lg.out_s)}
@@ -685,6 +707,8 @@ def main():
                     rf = lg.roofline(lg.stage_profile(2), prs, pes, wk)
                     out["hbm_equiv"] = {"achieved": rf["achieved"], "peak": rf["peak"], "unit": "GB/s", "frac": rf["frac"]}
                     out["tensor_frac"] = rf["tensor"]["frac"]
+                    out["smem_data_pipe_frac"] = rf["smem_data_pipe"]["frac"]
+                    out["clocks_per_group_per_sm"] = rf["smem_data_pipe"]["clocks_per_group_per_sm"]
                     out["stage_ms"] = rf["stage_ms"]
                     out["pairs_per_step"], out["pair_embeddings_per_step"] = prs, pes
                     if not args.no_gate:

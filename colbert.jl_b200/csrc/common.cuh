@@ -148,6 +148,7 @@ struct cb_index {
 
   // stats of the last search
   long long st_launches = 0;
+  double st_tc_groups = 0, st_tc_group_rows = 0, st_tc_passage_rows = 0;
   double st_pairs = 0, st_pair_embs = 0, st_flagged = 0, st_tc_pairs = 0, st_generic_pairs = 0, st_s1_tc_rows = 0, st_rescore_unsafe = 0, st_bad_cells = 0;
   double st_ms[5] = {0, 0, 0, 0, 0};  // stage1, stage2, stage34, stage5, total
   double st_plaid_survivors = 0, st_plaid_positive = 0, st_plaid_rescored = 0;
@@ -157,6 +158,8 @@ struct cb_index {
 // ---------------------------------------------------------------------------------------------
 // stage launchers (defined in the stage*.cu files)
 // ---------------------------------------------------------------------------------------------
+constexpr size_t CB_STATS_BYTES = 128;   // 16 batch counters: 0 pairs, 1 pair embeddings, 2 flagged rows, 3 range flag, 4 bad cells, 5 rescore-unsafe,
+                                         // 6 tcgen05 groups, 7 operand rows summed over groups, 8 operand rows summed over decompressed passages
 inline unsigned long long* cb_stats_dev(cb_index* ix) { return ix->d_stats.as<unsigned long long>(); }
 
 // Stage 1: per query-token row, the top-`nprobe` centroids of Q . C^T (exact fp32 decision).

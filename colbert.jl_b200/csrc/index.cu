@@ -334,12 +334,12 @@ static int32_t create_impl(cb_index* ix, const float* centroids, const float* bu
     CB_CUDA(cudaMemcpy(&h, d_max, sizeof(h), cudaMemcpyDeviceToHost));
     ix->max_cell_len = (int64_t)h;
   }
-  CB_TRY(ix->d_stats.ensure(64));
-  CB_CUDA(cudaMemset(ix->d_stats.p, 0, 64));
+  CB_TRY(ix->d_stats.ensure(CB_STATS_BYTES));
+  CB_CUDA(cudaMemset(ix->d_stats.p, 0, CB_STATS_BYTES));
   CB_TRY(ix->q_flag.ensure(sizeof(int)));
   CB_CUDA(cudaMemset(ix->q_flag.p, 0, sizeof(int)));
-  CB_CUDA(cudaHostAlloc((void**)&ix->pinned_stats, 64, cudaHostAllocDefault));
-  memset(ix->pinned_stats, 0, 64);
+  CB_CUDA(cudaHostAlloc((void**)&ix->pinned_stats, CB_STATS_BYTES, cudaHostAllocDefault));
+  memset(ix->pinned_stats, 0, CB_STATS_BYTES);
   CB_CUDA(cudaEventCreateWithFlags(&ix->ev_stats, cudaEventDisableTiming));
   CB_CUDA(cudaHostAlloc((void**)&ix->pinned_total, 64, cudaHostAllocDefault));
   for (auto& e : ix->ev) CB_CUDA(cudaEventCreate(&e));
@@ -420,6 +420,7 @@ extern "C" int32_t cb_get_stat(const cb_index* cix, const char* key, double* val
     ix->st_tc_pairs = (ix->stats_tc_selected && h[3] == 0) ? (double)h[0] : 0.0;
     ix->st_generic_pairs = (double)h[0] - ix->st_tc_pairs;
     ix->st_bad_cells = (double)h[4]; ix->st_rescore_unsafe = (double)h[5];
+    ix->st_tc_groups = (double)h[6]; ix->st_tc_group_rows = (double)h[7]; ix->st_tc_passage_rows = (double)h[8];
   }
   if (!strcmp(key, "launches")) *value = (double)ix->st_launches;
   else if (!strcmp(key, "pairs")) *value = ix->st_pairs;
@@ -430,6 +431,9 @@ extern "C" int32_t cb_get_stat(const cb_index* cix, const char* key, double* val
   else if (!strcmp(key, "plaid_candidates")) *value = ix->st_plaid_positive;
   else if (!strcmp(key, "plaid_rescored")) *value = ix->st_plaid_rescored;
   else if (!strcmp(key, "generic_pairs")) *value = ix->st_generic_pairs;
+  else if (!strcmp(key, "tc_groups")) *value = ix->st_tc_groups;
+  else if (!strcmp(key, "tc_group_rows")) *value = ix->st_tc_group_rows;
+  else if (!strcmp(key, "tc_passage_rows")) *value = ix->st_tc_passage_rows;
   else if (!strcmp(key, "rescore_unsafe")) *value = ix->st_rescore_unsafe;
   else if (!strcmp(key, "bad_cells")) *value = ix->st_bad_cells;
   else if (!strcmp(key, "max_cell_len")) *value = (double)ix->max_cell_len;

@@ -278,7 +278,7 @@ extern "C" int32_t cb_search_batch_plaid_device(cb_index* ix, const float* dQ, i
   const long long launches0 = g_cb_launches;
   ix->st_pairs = ix->st_pair_embs = ix->st_flagged = ix->st_tc_pairs = ix->st_generic_pairs = ix->st_s1_tc_rows = 0;
   ix->st_plaid_survivors = ix->st_plaid_positive = ix->st_plaid_rescored = 0;
-  CB_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 64, st));
+  CB_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, CB_STATS_BYTES, st));
   for (int q0 = 0; q0 < nq; q0 += CB_NQ_CHUNK) {
     const int n = (nq - q0 < CB_NQ_CHUNK) ? nq - q0 : CB_NQ_CHUNK;
     const int W = (n + 31) / 32;

@@ -29,7 +29,7 @@ static int64_t cb_pair_bound(const cb_index* ix, int nq, int T, int nprobe) {
 constexpr int64_t CB_PAIR_BOUND_LIMIT = (int64_t)2 << 30;   // pairs (16 GB of keys): above this the list is sized exactly, with a host round trip
 
 static int32_t begin_batch_stats(cb_index* ix, cudaStream_t st) {
-  CB_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 64, st));   // (allocated with the index)
+  CB_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, CB_STATS_BYTES, st));   // (allocated with the index)
   return CB_OK;
 }
 
@@ -38,7 +38,7 @@ __global__ void k_note_range_flag(const int* __restrict__ flag, unsigned long lo
 }
 
 static int32_t end_batch_stats(cb_index* ix, cudaStream_t st) {
-  CB_CUDA(cudaMemcpyAsync(ix->pinned_stats, ix->d_stats.p, 64, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(ix->pinned_stats, ix->d_stats.p, CB_STATS_BYTES, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaEventRecord(ix->ev_stats, st));
   ix->stats_pending = true;
   return CB_OK;

@@ -111,21 +111,34 @@ constexpr int TC_NTA = 2;
 #ifndef TC_PROF
 #define TC_PROF 0
 #endif
+#ifndef TC_TRACE_EVENTS
+#define TC_TRACE_EVENTS 0xfff          // which events of the trace are compiled in (every probe costs its role ~100 clocks)
+#endif
 #if TC_PROF
+// TC_PROF bit 0: wait / busy accounting of every warp of every CTA (TCW, TCP_*); bit 1: event trace of CTA 0 (TCT)
 __device__ unsigned long long g_tc_prof[160 * 32 * 24];
 __shared__ unsigned long long s_prof[32 * 24];
+constexpr int TC_TRACE_G0 = 20000, TC_TRACE_N = 4096;   // steady state: groups TC_TRACE_G0 .. +4095: g_tc_trace[event][group] = clock64
+__device__ long long g_tc_trace[12 * TC_TRACE_N];
+#if TC_PROF & 1
 #define TCW(bar_, par_, tag_, ...)                                                          \
   do {                                                                                      \
     const long long t0_ = clock64();                                                        \
     ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__);                                        \
     if (lane == 0 || warp == 1) s_prof[warp * 24 + (tag_)] += (unsigned long long)(clock64() - t0_);   \
   } while (0)
-// event trace of CTA 0 (steady state: groups TC_TRACE_G0 .. +4095): g_tc_trace[event][group] = clock64
-constexpr int TC_TRACE_G0 = 20000, TC_TRACE_N = 4096;
-__device__ long long g_tc_trace[12 * TC_TRACE_N];
-#define TCT(ev_, g_) do { if (blockIdx.x == 0 && (lane == 0 || warp == 1) && (g_) >= TC_TRACE_G0 && (g_) < TC_TRACE_G0 + TC_TRACE_N) g_tc_trace[(ev_) * TC_TRACE_N + (g_) - TC_TRACE_G0] = clock64(); } while (0)
 #define TCP_BEGIN() const long long tp0_ = clock64()
 #define TCP_END(tag_) do { if (lane == 0 || warp == 1) s_prof[warp * 24 + (tag_)] += (unsigned long long)(clock64() - tp0_); } while (0)
+#else
+#define TCW(bar_, par_, tag_, ...) ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__)
+#define TCP_BEGIN() do {} while (0)
+#define TCP_END(tag_) do {} while (0)
+#endif
+#if TC_PROF & 2
+#define TCT(ev_, g_) do { if (((TC_TRACE_EVENTS >> (ev_)) & 1) && blockIdx.x == 0 && (lane == 0 || warp == 1) && (g_) >= TC_TRACE_G0 && (g_) < TC_TRACE_G0 + TC_TRACE_N) g_tc_trace[(ev_) * TC_TRACE_N + (g_) - TC_TRACE_G0] = clock64(); } while (0)
+#else
+#define TCT(ev_, g_) do {} while (0)
+#endif
 #else
 #define TCW(bar_, par_, tag_, ...) ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__)
 #define TCP_BEGIN() do {} while (0)
@@ -136,8 +149,8 @@ __device__ long long g_tc_trace[12 * TC_TRACE_N];
 struct Meta {            // one passage entry, written by the scheduler
   int ncand;             // candidate queries of the passage (< 0: end of stream)
   int L;                 // doclen
-  int nchunk;            // 1 or 2
-  int n0, n1;            // rows of chunk 0 / 1 (padded to 16)
+  int nchunk;            // 1 .. TC_MAX_CHUNKS
+  int n0, n1;            // rows of chunks 0 .. nchunk-2 / of the last chunk (padded to 16; n1 = 0 for one chunk)
   int pid;               // local 0-based pid
   uint32_t b_off;        // byte offset of the operand tile(s) in the ring
   uint32_t pad_;
@@ -160,6 +173,7 @@ struct TcParams {
   const uint8_t* qprep;           // query row image: [nq][8 KB]
   const uint32_t* bitmap; const int64_t* list_off; int32_t* cursors; uint64_t* pairs;
   const int32_t* pid_list; int64_t n_list;   // optional: only these passages (sparse bitmaps, e.g. the PLAID rescoring pass)
+  unsigned long long* stats;      // batch counters (cb_stats_dev): [6] groups, [7] operand rows over groups, [8] operand rows over passages
   const int* q_flag;              // != 0: the batch breaks the |query token| <= 255 precondition; the generic kernel scores it
 };
 
@@ -443,6 +457,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
   const int64_t first = blockIdx.x, stride = gridDim.x;
   uint32_t head = 0;             // next free byte of the ring
   int e = 0;                     // entry counter
+  unsigned long long n_groups = 0, n_group_rows = 0, n_passage_rows = 0;   // what this CTA pushes through the tensor pipe (batch counters)
   int tail = 0;                  // entries < tail are known to have released their tile
   // Everything the scheduler reads from global memory for passage p -- its extent, its bitmap words
   // and the extent of the passage whose packed bytes it will prefetch -- is requested TWO
@@ -489,6 +504,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     int nchunk, n0, n1;
     tc_tile_geometry(L, nchunk, n0, n1);
     const uint32_t bytes = (uint32_t)tc_total_rows(nchunk, n0, n1) * 256u;
+
     // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
     const int slot = e & (TC_NSLOT - 1);
     TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
@@ -525,6 +541,9 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     if (lane == 0) {
       m.ncand = ncand; m.L = L; m.nchunk = nchunk; m.n0 = n0; m.n1 = n1; m.pid = (int)p; m.b_off = off; m.e0 = e0;
     }
+    n_groups += (unsigned long long)((ncand + 3) >> 2);
+    n_group_rows += (unsigned long long)((ncand + 3) >> 2) * (bytes >> 8);
+    n_passage_rows += bytes >> 8;
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
     e++;
@@ -533,6 +552,9 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
   const int slot = e & (TC_NSLOT - 1);
   TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 3);
   if (lane == 0) { meta[slot].ncand = -1; ptx::mbar_arrive(&bar->meta_full[slot]); }
+  if (lane == 0 && P.stats != nullptr) {
+    atomicAdd(P.stats + 6, n_groups); atomicAdd(P.stats + 7, n_group_rows); atomicAdd(P.stats + 8, n_passage_rows);
+  }
 }
 
 // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
@@ -1009,7 +1031,7 @@ __device__ __forceinline__ void t2_loader_role(const TcParams& P, const TcCtx& S
         TCW(&bar->t2_aempty[(G - NA) & 1u][st], pph, 9);
         if (++pq == period) { pq = 0; pph ^= 1u; }
       }
-      if (li == 0) TCT(6, (int)G);
+      if (li == 0 && (G & 1u) == 0) TCT(6, (int)(G >> 1));
       uint64_t* const full = &bar->t2_afull[G & 1u][st];
       uint8_t* dst = a_tile0 + (size_t)st * TC_A_BYTES;
       G++;
@@ -1157,14 +1179,14 @@ k_maxsim_tc2(TcParams P) {
             }
             const uint32_t tile = own & 1u;
             TCW(&bar->l_afull[s][tile], (own >> 1) & 1u, 6);
-            TCT(0, gc);
+            if (s == 0) TCT(0, gc);
             own++;
             const uint32_t a_tmem = a_tmem0 + tile * T2_A_TCOLS;
             for (int ch = 0; ch < nchunk; ch++) {
               TCW(&bar->l_dempty[s], dpar, 7);
               dpar ^= 1u;
               ptx::tc_fence_after();
-              TCT(1, gc);
+              if (s == 0 && ch == 0) TCT(1, gc);
               const bool lastc = (nchunk > 1) && (ch == nchunk - 1);
               const uint32_t b_lo = b_lo0 + (uint32_t)(ch * n0) * 16u, kb = lastc ? kb1 : kb0, idesc = lastc ? idesc1 : idesc0;
               TCP_BEGIN();
@@ -1175,7 +1197,7 @@ k_maxsim_tc2(TcParams P) {
               }
               ptx::tc_commit(&bar->l_dfull[s]);
               TCP_END(16);
-              TCT(2, gc);
+              if (s == 0) TCT(2, gc);
             }
             gc++;
           }
@@ -1219,8 +1241,10 @@ k_maxsim_tc2(TcParams P) {
     // Query rows of group `c` : bulk-copy stage -> registers -> A tile `tile` of the lane (all four quarters do it whether or not
     // the group has a query in their slot: a stale row only produces an accumulator row nobody reads); the stage goes back to the
     // loaders, the tile is handed to the issuer.
+    uint32_t conv = 0, done = 0;            // own groups converted / scored
     auto convert = [&](const T2Cursor& c, uint32_t tile) __attribute__((always_inline)) {
       uint32_t r[64];                         // this thread's (query, token) row: 128 fp16 = 64 packed columns
+      if (warp == T2_WORK_WARP0) TCT(7, (int)conv);
       TCW(&bar->t2_afull[s][c.st], c.par, 14);
       const uint8_t* src = a_tile0 + (size_t)c.st * TC_A_BYTES + row_off;
 #pragma unroll
@@ -1230,6 +1254,7 @@ k_maxsim_tc2(TcParams P) {
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->t2_aempty[s][c.st]);
+      if (warp == T2_WORK_WARP0) TCT(8, (int)conv);
       const uint32_t a_addr = a_addr0 + tile * T2_A_TCOLS;
       ptx::tmem_st_32x32b_x32(a_addr, r);
       ptx::tmem_st_32x32b_x32(a_addr + 32, r + 32);
@@ -1237,6 +1262,7 @@ k_maxsim_tc2(TcParams P) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->l_afull[s][tile]);
+      if (warp == T2_WORK_WARP0) TCT(9, (int)conv);
     };
     // max over one chunk's accumulator columns
     auto read_chunk = [&](int ncol, float& m0, float& m1, float& m2, float& m3) __attribute__((always_inline)) {
@@ -1282,7 +1308,6 @@ k_maxsim_tc2(TcParams P) {
     cur_start(ec);
     cur_seek(ec, s, true, true, 10);
     cc = ec;
-    uint32_t conv = 0, done = 0;
     bool cc_end = false;
     [[maybe_unused]] int gc = 0;
     while (!ec.end) {
@@ -1303,13 +1328,13 @@ k_maxsim_tc2(TcParams P) {
         TCW(&bar->l_dfull[s], dpar, 11);
         dpar ^= 1u;
         ptx::tc_fence_after();
-        if (q4 == 0 && ch == 0) TCT(3, gc);
+        if (warp == T2_WORK_WARP0 && ch == 0) TCT(3, gc);
         read_chunk((TC_ABLATE & 2) ? 16 : ((nchunk > 1 && ch == nchunk - 1) ? m.n1 : m.n0), m0, m1, m2, m3);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar->l_dempty[s]);   // accumulator drained
       }
-      if (q4 == 0) TCT(4, gc);
+      if (warp == T2_WORK_WARP0) TCT(4, gc);
       const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 262144.0f));   // exact 2^-18 fixed-point sum (k_maxsim_tc)
       const int qi = ec.g * 4 + q4;
@@ -1321,7 +1346,7 @@ k_maxsim_tc2(TcParams P) {
         }
         if (++cnt == 32) flush();
       }
-      if (q4 == 0) TCT(5, gc);
+      if (warp == T2_WORK_WARP0) TCT(5, gc);
       gc++;
       done++;
       cur_skip(ec, true);
@@ -1440,6 +1465,7 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   P.qprep = ix->q_prep.as<uint8_t>(); P.bitmap = d_bitmap; P.list_off = d_list_off; P.cursors = d_cursors; P.pairs = d_pairs;
   P.pid_list = ix->tc_active_list; P.n_list = ix->tc_active_n;
   P.q_flag = ix->q_flag.as<int>();
+  P.stats = cb_stats_dev(ix);
   if (P.pid_list && P.n_list == 0) return CB_OK;
   int64_t grid = ix->sm_count;
   const int64_t n_items = P.pid_list ? P.n_list : ix->Np;

@@ -10,7 +10,7 @@ for spec in $SPECS; do
 import json
 try:
     d=json.load(open("gpurun_out/ab.json"))
-    print("$spec $wl", round(d["value"]), "QPS stage34 %.1f ms" % d["roofline"]["stage_ms"]["ms_stage34"], "stage1 %.2f" % d["roofline"]["stage_ms"]["ms_stage1"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"], flush=True)
+    print("$spec $wl", round(d["value"]), "QPS stage34 %.1f ms" % d["roofline"]["stage_ms"]["ms_stage34"], "stage1 %.2f" % d["roofline"]["stage_ms"]["ms_stage1"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"], "clk/group %.0f smem-pipe %.2f" % ((d["roofline"]["smem_data_pipe"]["clocks_per_group_per_sm"] or 0), (d["roofline"]["smem_data_pipe"]["frac"] or 0)), flush=True)
 except Exception as e:
     print("$spec $wl FAILED", e)
 PY
