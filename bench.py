@@ -588,7 +588,7 @@ def main():
         _buf = _np.zeros((160, 32, 24), dtype=_np.uint64)
         lib.cb_debug_tc_prof(_buf.ctypes.data_as(C.c_void_p))
         _np.save(os.environ["CB_TC_PROF_OUT"], _buf)
-        _tr = _np.zeros((12, 4096), dtype=_np.int64)
+        _tr = _np.zeros((16, 4096), dtype=_np.int64)
         lib.cb_debug_tc_trace(_tr.ctypes.data_as(C.c_void_p))
         _np.save(os.environ["CB_TC_PROF_OUT"].replace(".npy", "_trace.npy"), _tr)
     # kernels launched by this rank's library per step (+ the all-gathers / merge of the sharded path)

@@ -47,6 +47,12 @@ namespace {
 #ifndef TC_LANES
 #define TC_LANES 1                     // 2 = the two-lane kernel k_maxsim_tc2 (two MMA issuers, A operand in tensor memory, fused convert + epilogue workers)
 #endif
+#ifndef TC_NI_DBG
+#define TC_NI_DBG 0                    // debugging switches of the two-issuer path
+#endif
+#ifndef TC_NISSUE
+#define TC_NISSUE 1                    // MMA issuer threads: 2 = two warps issue alternate groups, each into its own accumulator(s) (see tc_issuer_role)
+#endif
 #ifndef TC_EPI_MODE
 #define TC_EPI_MODE ((TC_EPI_SETS > 1) ? 0 : 1)   // accumulator read-out: 0 = one 32-column load at a time, 1 = double-buffered, 2 = all loads of up to
 #endif                                              // 80 columns issued at once, ONE tcgen05.wait::ld, accumulator released before the fold
@@ -73,8 +79,11 @@ namespace {
 constexpr int TC_NEPI_WARPS = 4 * TC_EPI_SETS;
 constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first decompression warp
 constexpr int TC_DIM = 128, TC_T = 32;
-constexpr int TC_MAX_BROWS = (TC_LANES == 2) ? 128 : (TC_TMEM_A ? 192 : 240);   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
-constexpr int TC_MAX_CHUNKS = (TC_LANES == 2) ? 3 : 2;                          // chunks per passage (accumulator passes per group)
+#ifndef TC_NACC
+#define TC_NACC 2                      // TMEM accumulators (shared-memory A operand): 2 x 256 columns, or 4 x 128 so that the MMA issuer can run
+#endif                                 // three groups ahead of the epilogue (passages over 128 tokens then take up to 4 chunks)
+constexpr int TC_MAX_BROWS = (TC_LANES == 2) ? 128 : (TC_TMEM_A ? 192 : (TC_NACC == 4 ? 128 : 240));   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
+constexpr int TC_MAX_CHUNKS = (TC_LANES == 2) ? 3 : ((TC_NACC == 4 && !TC_TMEM_A) ? 4 : 2);           // chunks per passage (accumulator passes per group)
 constexpr int TC_MAX_ASTAGES = 6;
 #ifndef TC_NSLOT_LOG2
 #define TC_NSLOT_LOG2 2
@@ -84,12 +93,17 @@ constexpr int TC_A_BYTES = 128 * TC_DIM * 2;  // 32 KB: 4 queries x 32 tokens x 
 constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                    // measurement-only builds (results are garbage): 1 = one 8 KB query copy per group instead of
-#endif                                 // four, 2 = epilogue reads 16 accumulator columns, 4 = no decompression, 8 = 2 of 8 MMA K-steps
+#endif                                 // four, 2 = epilogue reads 16 accumulator columns, 4 = no decompression, 8 = 2 of 8 MMA K-steps, 16 = no pair append, 32 = no L2 prefetch of packed bytes
 #ifndef TC_NLOAD
 #define TC_NLOAD 2                     // query-tile loader warps (2: warps 2-3; 4: two more taken from the decompression pool)
 #endif
-constexpr int TC_NDEC_WARPS = 8 - (TC_NLOAD - 2);
-constexpr int TC_DEC_FIRST = TC_DEC_WARP0 + (TC_NLOAD - 2);   // first decompression warp (loaders 2.. sit before it)
+constexpr int TC_NXISS = (TC_NISSUE == 2) ? 2 : 0;               // warps set aside for the second issuer (the first of them issues, the other idles)
+#ifndef TC_NDEC_WARPS_
+#define TC_NDEC_WARPS_ (8 - (TC_NLOAD - 2) - TC_NXISS)   // default: 16 warps in all (512 threads)
+#endif
+constexpr int TC_NDEC_WARPS = TC_NDEC_WARPS_;
+constexpr int TC_XISS_WARP0 = TC_DEC_WARP0 + (TC_NLOAD - 2);     // second issuer's warp (loaders 2.. sit before it)
+constexpr int TC_DEC_FIRST = TC_XISS_WARP0 + TC_NXISS;           // first decompression warp
 #ifndef TC_NTEAMS_
 #define TC_NTEAMS_ 2
 #endif
@@ -103,7 +117,8 @@ template <int N> __device__ __forceinline__ void tc_reg_budget() {   // a role's
 }
 // tensor memory: two accumulators of TC_D_COLS fp32 columns; with TC_TMEM_A also TC_NTA query-tile stages of 64 columns
 // (128 lanes x 128 fp16 = 64 packed 32-bit columns: lane = (query, token) row, column j = dims 2j, 2j+1)
-constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = TC_TMEM_A ? 192 : 256, TC_A_COL0 = 2 * TC_D_COLS, TC_A_TCOLS = 64;
+constexpr int TC_NACC_ = TC_TMEM_A ? 2 : TC_NACC;   // accumulators in use
+constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = TC_TMEM_A ? 192 : 512 / TC_NACC_, TC_A_COL0 = 2 * TC_D_COLS, TC_A_TCOLS = 64;
 constexpr int TC_NTA = 2;
 
 // Measurement-only build (-DTC_PROF=1): every mbarrier wait is timed with clock64 and charged to (warp, wait tag); slot 0 of a
@@ -118,8 +133,9 @@ constexpr int TC_NTA = 2;
 // TC_PROF bit 0: wait / busy accounting of every warp of every CTA (TCW, TCP_*); bit 1: event trace of CTA 0 (TCT)
 __device__ unsigned long long g_tc_prof[160 * 32 * 24];
 __shared__ unsigned long long s_prof[32 * 24];
-constexpr int TC_TRACE_G0 = 20000, TC_TRACE_N = 4096;   // steady state: groups TC_TRACE_G0 .. +4095: g_tc_trace[event][group] = clock64
-__device__ long long g_tc_trace[12 * TC_TRACE_N];
+constexpr int TC_TRACE_G0 = 20000, TC_TRACE_N = 4096, TC_TRACE_E0 = 4700;   // per-passage events (TCE, rows 7-11): entries TC_TRACE_E0 .. +4095
+  // steady state: groups TC_TRACE_G0 .. +4095: g_tc_trace[event][group] = clock64
+__device__ long long g_tc_trace[16 * TC_TRACE_N];
 #if TC_PROF & 1
 #define TCW(bar_, par_, tag_, ...)                                                          \
   do {                                                                                      \
@@ -136,14 +152,17 @@ __device__ long long g_tc_trace[12 * TC_TRACE_N];
 #endif
 #if TC_PROF & 2
 #define TCT(ev_, g_) do { if (((TC_TRACE_EVENTS >> (ev_)) & 1) && blockIdx.x == 0 && (lane == 0 || warp == 1) && (g_) >= TC_TRACE_G0 && (g_) < TC_TRACE_G0 + TC_TRACE_N) g_tc_trace[(ev_) * TC_TRACE_N + (g_) - TC_TRACE_G0] = clock64(); } while (0)
+#define TCE(ev_, e_) do { if (blockIdx.x == 0 && lane == 0 && (e_) >= TC_TRACE_E0 && (e_) < TC_TRACE_E0 + TC_TRACE_N) g_tc_trace[(ev_) * TC_TRACE_N + (e_) - TC_TRACE_E0] = clock64(); } while (0)
 #else
 #define TCT(ev_, g_) do {} while (0)
+#define TCE(ev_, e_) do {} while (0)
 #endif
 #else
 #define TCW(bar_, par_, tag_, ...) ptx::mbar_wait(bar_, par_, tag_, ##__VA_ARGS__)
 #define TCP_BEGIN() do {} while (0)
 #define TCP_END(tag_) do {} while (0)
 #define TCT(ev_, g_) do {} while (0)
+#define TCE(ev_, e_) do {} while (0)
 #endif
 
 struct Meta {            // one passage entry, written by the scheduler
@@ -161,7 +180,7 @@ struct Meta {            // one passage entry, written by the scheduler
 struct Barriers {
   uint64_t b_full[TC_NSLOT], b_empty[TC_NSLOT], meta_full[TC_NSLOT], meta_empty[TC_NSLOT];
   uint64_t a_full[TC_MAX_ASTAGES], a_empty[TC_MAX_ASTAGES];
-  uint64_t d_full[TC_EPI_SETS][2], d_empty[2];
+  uint64_t d_full[TC_EPI_SETS][4], d_empty[4];
   uint64_t at_full[TC_NTA], at_empty[TC_NTA];   // query-tile stages in tensor memory (TC_TMEM_A)
   uint64_t l_afull[2][2], l_dempty[2], l_dfull[2];   // two-lane kernel: lane's A tile t holds a group / accumulator drained / MMAs retired
   uint64_t t2_afull[2][TC_MAX_ASTAGES], t2_aempty[2][TC_MAX_ASTAGES];   // two-lane kernel: bulk-copy stage barriers PER LANE (see t2_loader_role)
@@ -413,7 +432,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
     for (int i = 0; i < TC_DBATCH; i++) {
       if (i < per && j0 + i < nround) {   // warp-uniform
         const int rr = rr0 + 4 * TEAM_WARPS * (j0 + i);
-        const int c = (rr >= n0 ? 1 : 0) + (rr >= 2 * n0 ? 1 : 0);        // chunk of this row (nchunk <= 3)
+        const int c = (rr >= n0 ? 1 : 0) + (rr >= 2 * n0 ? 1 : 0) + (rr >= 3 * n0 ? 1 : 0);   // chunk of this row (nchunk <= 4)
         finish_token16<NBITS, DUMP>(lut_lane, bits[i], cr[i], l8, tile0 + c * n0 * 256, ((nchunk > 1 && c == nchunk - 1) ? n1 : n0) * 128, rr - c * n0,
                                     (DUMP && rr < L) ? raw_out + (size_t)rr * TC_DIM : nullptr);
       }
@@ -438,6 +457,7 @@ __device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S
   Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const a_tile0 = S.a_tile0; const int NA = S.NA;
   (void)warp;
   uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
+  [[maybe_unused]] uint32_t turn = 0;   // TC_NISSUE == 2: issuer of the current group
   [[maybe_unused]] int gc = 0;
   for (int e = 0;; e++) {
     const int slot = e & (TC_NSLOT - 1);
@@ -452,23 +472,105 @@ __device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S
       TCW(&bar->a_empty[st_g], par_g, 9);
       if (li == 0) TCT(6, gc);
       gc++;
+      // With two issuers the "tile landed" barrier of a stage is the one of the group's ISSUER: a waiter must observe every phase
+      // of a barrier it waits on, in order (an issuer asking for its group G while the stage's previous tile, the other issuer's
+      // group G - NA, has not landed yet would take the phase of G - 2 NA -- same parity -- for its own).
+#if TC_NISSUE == 2
+      uint64_t* const full = &bar->t2_afull[turn][st_g];
+      turn ^= 1u;
+#else
+      uint64_t* const full = &bar->a_full[st_g];
+#endif
       const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
       uint8_t* dst = a_tile0 + (size_t)st_g * TC_A_BYTES;
       const int nmine = (nqg - li + NLOAD - 1) / NLOAD;      // queries li, li + NLOAD, ... < nqg
       if (nmine <= 0) {
-        if (ptx::elect_one()) ptx::mbar_arrive(&bar->a_full[st_g]);
+        if (ptx::elect_one()) ptx::mbar_arrive(full);
         continue;
       }
       const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * NLOAD] : 0;   // lane i holds this loader's i-th query
-      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&bar->a_full[st_g], (uint32_t)nmine * TC_Q_BYTES);
+      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full, (uint32_t)nmine * TC_Q_BYTES);
       for (int i = 0; i < nmine; i++) {
         const int q = __shfl_sync(0xffffffffu, qv, i);
         if (ptx::elect_one())
-          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, &bar->a_full[st_g]);
+          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full);
       }
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
+  }
+}
+
+// ===== MMA issue by TC_NISSUE = 2 threads (shared-memory A operand).  Why: tcgen05.mma issue is asynchronous only up to a queue
+// of ~6 instructions, and ONE thread needs more time per 4-query group than the tensor pipe (8 MMAs = ~420 clocks at N = 80): two
+// mbarrier probes of ~100 clocks each (try_wait + dependent branch, even when the phase completed long ago), ~50 uniform-datapath
+// instructions of descriptor arithmetic, three commits.  tools/pipe_skeleton.cu isolates it: the same loop with loop-invariant
+// descriptors and no waits runs at 416 clocks per group, with per-group descriptors and the two waits at 680-730, and with two
+// issuers on alternate groups at ~510-550 again.  Issuer `me` takes the groups G = me (mod 2) of the CTA's running group count
+// into its own accumulator(s) me, me + 2, ...; both walk every passage and keep the stage / group counters of all groups.  A
+// passage's tile is released by BOTH (b_empty counts 2: a commit covers "all my earlier MMAs", also when none read this tile),
+// and both are among the arrivals that release its meta slot (an issuer without a group in the passage could otherwise still
+// be about to read a slot the scheduler has republished). =====
+__device__ __forceinline__ void tc_issuer_role(const TcCtx& S, const uint32_t tmem_base, const int me, const int warp, const int lane) {
+  Barriers* const bar = S.bar; Meta* const meta = S.meta; const int NA = S.NA;
+  (void)warp; (void)lane;
+  constexpr int NI = 2, ACC_PER = TC_NACC_ / NI;
+  const uint32_t a_lo0 = ((ptx::smem_u32(S.a_tile0) & 0x3ffffu) >> 4) | (1u << 16);   // descriptor low words: start address >> 4, LBO field = 1
+  const uint32_t ring_lo = ((ptx::smem_u32(S.ring) & 0x3ffffu) >> 4) | (1u << 16);
+  constexpr uint32_t HI_A = (2048u >> 4) | (1u << 14) | (2u << 29);   // SBO 2048 | version 1 | SWIZZLE_128B
+  constexpr uint32_t HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024
+  const uint32_t period = (NA & 1) ? 2u * (uint32_t)NA : (uint32_t)NA;   // barrier (issuer, stage) serves every lcm(2, NA)-th group
+  uint32_t st = 0, pq = 0, a_par = 0;   // query-tile stage of the running group G / G % period / parity of phase G / period of its a_full barrier
+  uint32_t ka = 0, d_par = 1;        // own accumulator me + NI * ka / parity of the next d_empty phase of the own accumulators
+  uint32_t turn = 0;                 // running group count mod NI
+  [[maybe_unused]] int gc = 0;
+  for (int e = 0;; e++) {
+    const int slot = e & (TC_NSLOT - 1);
+    const uint32_t ph = (e >> TC_NSLOT_LOG2) & 1;
+    TCW(&bar->meta_full[slot], ph, 4);
+    const int ncand = meta[slot].ncand;
+    if (ncand < 0) break;
+    const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
+    const uint32_t b_lo0 = ring_lo + (meta[slot].b_off >> 4);
+    const uint32_t kb0 = (uint32_t)n0 * 8u, kb1 = (uint32_t)n1 * 8u;   // K-block stride (rows * 128 B) >> 4
+    const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
+    const int ngroups = (ncand + 3) >> 2;
+    bool waited = false;
+    for (int g = 0; g < ngroups; g++) {
+      const bool mine = turn == (uint32_t)me;
+      turn = (turn + 1u) & (uint32_t)(NI - 1);
+      const uint32_t st_g = st, par_g = a_par;
+      if (++st == (uint32_t)NA) st = 0;
+      if (++pq == period) { pq = 0; a_par ^= 1u; }
+      if (!mine) { gc++; continue; }
+      if (!waited) { TCW(&bar->b_full[slot], ph, 5); waited = true; }
+      TCW(&bar->t2_afull[me][st_g], par_g, 6);
+      TCT(0, gc);
+      const uint32_t a_lo = a_lo0 + st_g * (uint32_t)(TC_A_BYTES >> 4);
+      for (int c = 0; c < nchunk; c++) {
+        const uint32_t ds = (uint32_t)me + (uint32_t)NI * ka;
+        TCW(&bar->d_empty[ds], d_par, 7);
+        ptx::tc_fence_after();
+        TCT(1, gc);
+        const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
+        const bool lastc = c > 0 && c == nchunk - 1;                   // chunk c starts c * n0 * 256 bytes in; the last of several has n1 rows
+        const uint32_t b_lo = b_lo0 + (uint32_t)c * (uint32_t)n0 * 16u, kb = lastc ? kb1 : kb0, idesc = lastc ? idesc1 : idesc0;
+#pragma unroll
+        for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
+          const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
+          const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
+          ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st_g]);
+        ptx::tc_commit(&bar->d_full[TC_EPI_SETS == 2 ? me : 0][ds]);
+        TCT(2, gc);
+        if (++ka == (uint32_t)ACC_PER) { ka = 0; d_par ^= 1u; }
+      }
+      gc++;
+    }
+    if ((TC_NI_DBG & 2) && !waited) ptx::mbar_arrive(&bar->b_empty[slot]);
+    else ptx::tc_commit(&bar->b_empty[slot]);   // arrives after this thread's earlier MMAs have retired (none of them may have read this tile)
+    if (!(TC_NI_DBG & 1)) ptx::mbar_arrive(&bar->meta_empty[slot]);
   }
 }
 
@@ -513,7 +615,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     const int64_t e0 = h.o0;
     const int L = (int)(h.o1 - h.o0);
     uint32_t w = h.w;
-    if (h.f1 > h.f0) {
+    if (h.f1 > h.f0 && !(TC_ABLATE & 32)) {
       const char* r0 = reinterpret_cast<const char*>(P.residuals) + h.f0 * P.R;
       const char* c0 = reinterpret_cast<const char*>(P.codes) + h.f0 * 4;
       const int64_t rbytes = (h.f1 - h.f0) * P.R, cbytes = (h.f1 - h.f0) * 4;
@@ -530,6 +632,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
     const int slot = e & (TC_NSLOT - 1);
     TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
+    TCE(7, e);
     if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
     // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps.  The
     // regions of the last TC_NSLOT entries sit in shared memory (dynamically indexed local arrays
@@ -568,6 +671,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     n_passage_rows += bytes >> 8;
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&bar->meta_full[slot]);
+    TCE(8, e);
     e++;
   }
   // end of stream
@@ -611,6 +715,7 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
     if (stop) break;
     const int slot = e & (TC_NSLOT - 1);
     const Meta& m = meta[slot];
+    if (dw == 0) TCE(9, e);
     // The first codes of the team's NEXT passage are requested now, if the scheduler has already published it (the usual case:
     // it runs up to TC_NSLOT entries ahead), so that one of the two dependent global round trips of a passage (codes -> centroid
     // rows) overlaps the expansion of this one.  The peek does not consume the entry: the probe loop above still does.
@@ -635,6 +740,7 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
+    if (dw == 0) TCE(10, e);
   }
 }
 
@@ -666,14 +772,15 @@ k_maxsim_tc(TcParams P) {
 
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
-      ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], 1);
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + (TC_TMEM_A ? 4 : 0));
+      ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], TC_NISSUE);
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + (TC_TMEM_A ? 4 : 0) + ((TC_NISSUE == 2 && !(TC_NI_DBG & 1)) ? 2 : 0));
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < TC_NACC_; i++) {
       for (int s = 0; s < TC_EPI_SETS; s++) ptx::mbar_init(&bar->d_full[s][i], 1);
       ptx::mbar_init(&bar->d_empty[i], 4);
     }
     for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], TC_TMEM_A ? 4 : 1); }
+    if (TC_NISSUE == 2) for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->t2_afull[0][i], TC_NLOAD); ptx::mbar_init(&bar->t2_afull[1][i], TC_NLOAD); }
     for (int i = 0; i < TC_NTA; i++) { ptx::mbar_init(&bar->at_full[i], 4); ptx::mbar_init(&bar->at_empty[i], 1); }
     ptx::fence_barrier_init();
   }
@@ -702,6 +809,9 @@ k_maxsim_tc(TcParams P) {
     // stage and parity counters are carried incrementally and every descriptor is a precomputed low
     // word plus a constant, so a group costs a few dozen instructions.  The issuer is the serial
     // resource of the kernel: at N = 80 a group's 8 MMAs are only ~320 tensor clocks. =====
+#if TC_NISSUE == 2
+    if (ptx::elect_one()) tc_issuer_role(S, tmem_base, 0, warp, lane);
+#else
     if (ptx::elect_one()) {
       [[maybe_unused]] const uint32_t a_lo0 = ((ptx::smem_u32(a_tile0) & 0x3ffffu) >> 4) | (1u << 16);   // descriptor low words: start
       const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);    // address >> 4, LBO field = 1
@@ -719,7 +829,6 @@ k_maxsim_tc(TcParams P) {
         if (ncand < 0) break;
         const int nchunk = meta[slot].nchunk, n0 = meta[slot].n0, n1 = meta[slot].n1;
         const uint32_t b_lo0 = ring_lo + (meta[slot].b_off >> 4);
-        const uint32_t b_lo1 = b_lo0 + (uint32_t)n0 * 16u;                 // chunk 1 starts n0 * 256 bytes in
         const uint32_t kb0 = (uint32_t)n0 * 8u, kb1 = (uint32_t)n1 * 8u;   // K-block stride (rows * 128 B) >> 4
         const uint32_t idesc0 = ptx::idesc_f16(128, n0, 0), idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
         const int ngroups = (ncand + 3) >> 2;
@@ -738,7 +847,8 @@ k_maxsim_tc(TcParams P) {
             ptx::tc_fence_after();
             TCT(1, gc);
             const uint32_t d_tmem = tmem_base + ds * TC_D_COLS;
-            const uint32_t b_lo = c ? b_lo1 : b_lo0, kb = c ? kb1 : kb0, idesc = c ? idesc1 : idesc0;
+            const bool lastc = c > 0 && c == nchunk - 1;                   // chunk c starts c * n0 * 256 bytes in; the last of several has n1 rows
+            const uint32_t b_lo = b_lo0 + (uint32_t)c * (uint32_t)n0 * 16u, kb = lastc ? kb1 : kb0, idesc = lastc ? idesc1 : idesc0;
             TCP_BEGIN();
 #pragma unroll
             for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
@@ -758,7 +868,7 @@ k_maxsim_tc(TcParams P) {
             ptx::tc_commit(&bar->d_full[eset][ds]);
             TCP_END(16);
             TCT(2, gc);
-            ds ^= 1u;
+            ds = (ds + 1u) & (uint32_t)(TC_NACC_ - 1);
             d_par ^= (ds == 0u) ? 1u : 0u;
           }
           if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
@@ -768,6 +878,7 @@ k_maxsim_tc(TcParams P) {
         ptx::tc_commit(&bar->b_empty[slot]);   // arrives after the passage's last MMA retires
       }
     }
+#endif
     __syncwarp();
   } else {
     tc_loader_role<TC_NLOAD>(P, S, warp - 2, warp, lane);
@@ -779,6 +890,7 @@ k_maxsim_tc(TcParams P) {
     const uint32_t myset = (uint32_t)(warp - 4) >> 2;   // this warp's set scores groups ug % TC_EPI_SETS == myset
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     uint32_t ud = 0, eset = 0;
+    [[maybe_unused]] uint32_t turn = 0, udi0 = 0, udi1 = 0;   // TC_NISSUE == 2: issuer of the running group / accumulator passes of each issuer so far
     uint32_t fpar = 0;                      // bit ds = parity of this set's next phase of d_full[myset][ds]
     // Output batching: the (query, key) record of the r-th scored pair of this warp is parked in
     // lane r % 32; every 32 records the whole warp appends them to the per-query lists with 32
@@ -813,11 +925,21 @@ k_maxsim_tc(TcParams P) {
       for (int g = 0; g < ngroups; g++) {
         const bool mine = (eset == myset);
         if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
+#if TC_NISSUE == 2
+        const uint32_t iss = turn;
+        turn ^= 1u;
+        if (!mine) { if (iss) udi1 += nchunk; else udi0 += nchunk; }
+#endif
         if (!mine) { ud += nchunk; gc++; continue; }
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 chains: ILP for the ALU pipe
         for (int c = 0; c < nchunk; c++, ud++) {
-          const int ds = ud & 1;
-          const int ncol = (TC_ABLATE & 2) ? 16 : (c ? n1 : n0);
+#if TC_NISSUE == 2
+          const int ds = (int)(iss + 2u * ((iss ? udi1 : udi0) & (uint32_t)(TC_NACC_ / 2 - 1)));   // issuer iss cycles over accumulators iss, iss + 2, ...
+          if (iss) udi1++; else udi0++;
+#else
+          const int ds = ud & (TC_NACC_ - 1);
+#endif
+          const int ncol = (TC_ABLATE & 2) ? 16 : ((c > 0 && c == nchunk - 1) ? n1 : n0);
           const int nfull = ncol >> 5;           // full 32-column chunks (<= 7)
           TCW(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11);
           fpar ^= 1u << ds;
@@ -897,7 +1019,7 @@ k_maxsim_tc(TcParams P) {
         // absolute on a score, far inside the 1e-3 relative tolerance.
         const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 262144.0f));
         const int qi = g * 4 + q4;
-        if (qi < ncand) {
+        if (qi < ncand && !((TC_ABLATE & 16) && isum != 0x7fffffff)) {
           const float score = (float)isum * (1.0f / 262144.0f);
           if (lane == (cnt & 31)) {
             my_q = m.q[qi];
@@ -976,8 +1098,12 @@ k_maxsim_tc(TcParams P) {
     }
   } else {
     tc_reg_budget<TC_REG_DEC>();
-    if (warp < TC_DEC_FIRST) {
+    if (warp < TC_XISS_WARP0) {
       tc_loader_role<TC_NLOAD>(P, S, warp - TC_DEC_WARP0 + 2, warp, lane);
+    } else if (warp < TC_DEC_FIRST) {
+#if TC_NISSUE == 2
+      if (warp == TC_XISS_WARP0) { if (ptx::elect_one()) tc_issuer_role(S, tmem_base, 1, warp, lane); __syncwarp(); }
+#endif
     } else {
     // ===== decompression: packed codes/residuals -> normalised fp16 operand tile(s) =====
     // Eight lanes per token, four tokens per warp-round (fewer, wider instructions per token than a
@@ -1560,9 +1686,9 @@ extern "C" int32_t cb_debug_tc_prof(unsigned long long* out /* [160][32][24] */)
   CB_CUDA(cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 160 * 32 * 24));
   return CB_OK;
 }
-extern "C" int32_t cb_debug_tc_trace(long long* out /* [12][4096] */) {
+extern "C" int32_t cb_debug_tc_trace(long long* out /* [16][4096] */) {
   CB_CUDA(cudaDeviceSynchronize());
-  CB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 12 * TC_TRACE_N));
+  CB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 16 * TC_TRACE_N));
   return CB_OK;
 }
 #endif
