@@ -20,17 +20,17 @@
 //     query tokens" is one warp reduction.  Padded token rows duplicate the last real token, so
 //     no column masking is needed.  Passages of 241..480 tokens are two chunks (two accumulators,
 //     one running maximum).
-//   * What bounds it: every (query, passage) pair pulls its 8 KB query tile L2 -> SM, and the chip
-//     sustains ~8.7 TB/s of that (~34 B/clk/SM; the same rate in eight structurally different
-//     builds of this kernel), i.e. ~950 clocks per 4-query group; the MMA of a
-//     group is 320-544 clocks and every other role has slack, so the kernel is built to keep that
-//     stream saturated: query tiles 3 groups ahead, passages up to 4 ahead, the scheduler's own
-//     global reads two passages ahead.
-//   * Warp-specialised, mbarrier-pipelined: warp 0 = scheduler (candidate lists, ring allocation),
-//     warp 1 = MMA issuer (one thread), warps 2-3 = query-tile loaders, warps 4-7 = epilogue (one
-//     TMEM lane quarter each), warps 8-15 = decompression.  Pipelines: passage entries (4 meta
-//     slots + a variable-size shared-memory ring of operand tiles), query tiles (3-4 stages), TMEM
-//     accumulators (2 x 256 columns).
+//   * What bounds it (measured): the SM's 128 B/clk shared-memory / L1 data pipe.  A 4-query group moves
+//     ~95 KB through it (32 KB bulk-copy write + 32 KB operand read of the query tile, 8 x N x 32 B of passage tile, ~25 KB of
+//     decompression loads / stores / table reads) = ~750 clocks; the kernel runs at ~900 clocks per group (83 % of the pipe),
+//     with the SM clock at 1.63-1.67 GHz under the 1000 W power cap.  In isolation (tools/pipe_skeleton.cu) the same MMAs,
+//     copies and accumulator reads take 416-550 clocks per group; getting from ~1040 (one MMA issuer, one epilogue set) to ~900
+//     took doubling every serial role at once: each of them alone sat at ~800-1000 clocks of its own latency per group.
+//   * Warp-specialised, mbarrier-pipelined, 22 warps: warp 0 = scheduler (candidate lists, ring allocation), warps 1 and 12 =
+//     MMA issuers (one thread each, alternate groups, one accumulator each), warps 2-3 = query-tile loaders, warps 4-7 and 8-11
+//     = two epilogue sets (one TMEM lane quarter per warp; set s reads issuer s's accumulator), warp 13 idle, warps 14-21 =
+//     decompression (two teams on alternate passages).  Pipelines: passage entries (4 meta slots + a variable-size
+//     shared-memory ring of operand tiles), query tiles (3 stages of 32 KB), TMEM accumulators (2 x 256 columns).
 // Requires dim = 128, T = 32, nbits in {1, 2, 4}; longer passages and every other shape are scored
 // by the generic kernel (stage34_generic.cu).
 #include "common.cuh"
@@ -39,51 +39,47 @@
 namespace {
 
 #ifndef TC_EPI_SETS
-#define TC_EPI_SETS 1                  // epilogue warp sets (each set = 4 warps = one accumulator consumer)
+#define TC_EPI_SETS 2                  // epilogue warp sets (each set = 4 warps); with two issuers set s reads issuer s's accumulator(s)
 #endif
-#ifndef TC_TMEM_A
-#define TC_TMEM_A 0                    // 1 = the A operand (query tiles) is forwarded shared memory -> registers -> TENSOR MEMORY by
-#endif                                 // four converter warps and tcgen05.mma reads it from there (see "what bounds it" above); 0 = A from shared memory
-#ifndef TC_LANES
-#define TC_LANES 1                     // 2 = the two-lane kernel k_maxsim_tc2 (two MMA issuers, A operand in tensor memory, fused convert + epilogue workers)
+#ifndef TC_BACKOFF_NS
+#define TC_BACKOFF_NS 0                // nanosleep between polls of the waits that are usually long and have slack (loaders: free stage, scheduler: slot / ring)
+#endif
+#ifndef TC_BACKOFF_EPI_NS
+#define TC_BACKOFF_EPI_NS 0            // ... of the epilogue's wait for an accumulator
+#endif
+#ifndef TC_BACKOFF_DEC_NS
+#define TC_BACKOFF_DEC_NS 20           // ... of the decompression warps' wait for the next passage
 #endif
 #ifndef TC_NI_DBG
 #define TC_NI_DBG 0                    // debugging switches of the two-issuer path
 #endif
 #ifndef TC_NISSUE
-#define TC_NISSUE 1                    // MMA issuer threads: 2 = two warps issue alternate groups, each into its own accumulator(s) (see tc_issuer_role)
+#define TC_NISSUE 2                    // MMA issuer threads: 2 = two warps issue alternate groups, each into its own accumulator(s) (see tc_issuer_role)
 #endif
 #ifndef TC_EPI_MODE
 #define TC_EPI_MODE ((TC_EPI_SETS > 1) ? 0 : 1)   // accumulator read-out: 0 = one 32-column load at a time, 1 = double-buffered, 2 = all loads of up to
 #endif                                              // 80 columns issued at once, ONE tcgen05.wait::ld, accumulator released before the fold
-// Register budget per warpgroup (setmaxnreg; 0 = leave the launch allocation).  The pool is threads x launch registers:
-// 512 x 128 (shared-memory A) or 640 x 96 (TC_TMEM_A); a budget must sum to at most that over the warpgroups.
+// Register budget per warpgroup (setmaxnreg; 0 = leave the launch allocation).  The pool is threads x launch registers; the
+// 704-thread default build (two issuers, two epilogue sets) runs every role inside the 80 registers of the launch allocation.
 #ifndef TC_REG_CTRL
-#if TC_EPI_SETS == 1 && !TC_TMEM_A
+#if TC_EPI_SETS == 1
 #define TC_REG_CTRL 96
 #define TC_REG_EPI 176
 #define TC_REG_DEC 120
-#define TC_REG_CONV 0
-#elif TC_EPI_SETS == 1 && TC_TMEM_A
-#define TC_REG_CTRL 56
-#define TC_REG_EPI 136
-#define TC_REG_DEC 0
-#define TC_REG_CONV 0
 #else
 #define TC_REG_CTRL 0
 #define TC_REG_EPI 0
 #define TC_REG_DEC 0
-#define TC_REG_CONV 0
 #endif
 #endif
 constexpr int TC_NEPI_WARPS = 4 * TC_EPI_SETS;
-constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first decompression warp
+constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first warp after the epilogue sets
 constexpr int TC_DIM = 128, TC_T = 32;
 #ifndef TC_NACC
 #define TC_NACC 2                      // TMEM accumulators (shared-memory A operand): 2 x 256 columns, or 4 x 128 so that the MMA issuer can run
 #endif                                 // three groups ahead of the epilogue (passages over 128 tokens then take up to 4 chunks)
-constexpr int TC_MAX_BROWS = (TC_LANES == 2) ? 128 : (TC_TMEM_A ? 192 : (TC_NACC == 4 ? 128 : 240));   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
-constexpr int TC_MAX_CHUNKS = (TC_LANES == 2) ? 3 : ((TC_NACC == 4 && !TC_TMEM_A) ? 4 : 2);           // chunks per passage (accumulator passes per group)
+constexpr int TC_MAX_BROWS = (TC_NACC == 4) ? 128 : 240;   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
+constexpr int TC_MAX_CHUNKS = (TC_NACC == 4) ? 4 : 2; // chunks per passage (accumulator passes per group)
 constexpr int TC_MAX_ASTAGES = 6;
 #ifndef TC_NSLOT_LOG2
 #define TC_NSLOT_LOG2 2
@@ -99,7 +95,7 @@ constexpr int TC_Q_BYTES = TC_T * TC_DIM * 2; // 8 KB per query
 #endif
 constexpr int TC_NXISS = (TC_NISSUE == 2) ? 2 : 0;               // warps set aside for the second issuer (the first of them issues, the other idles)
 #ifndef TC_NDEC_WARPS_
-#define TC_NDEC_WARPS_ (8 - (TC_NLOAD - 2) - TC_NXISS)   // default: 16 warps in all (512 threads)
+#define TC_NDEC_WARPS_ ((TC_NISSUE == 2) ? 8 : 8 - (TC_NLOAD - 2))   // two issuers: 22 warps in all (704 threads); else 16 (512 threads)
 #endif
 constexpr int TC_NDEC_WARPS = TC_NDEC_WARPS_;
 constexpr int TC_XISS_WARP0 = TC_DEC_WARP0 + (TC_NLOAD - 2);     // second issuer's warp (loaders 2.. sit before it)
@@ -108,18 +104,16 @@ constexpr int TC_DEC_FIRST = TC_XISS_WARP0 + TC_NXISS;           // first decomp
 #define TC_NTEAMS_ 2
 #endif
 constexpr int TC_NTEAMS = TC_NTEAMS_;   // decompression teams (round-robin over passages)
-constexpr int TC_CONV_WARP0 = TC_DEC_FIRST + TC_NDEC_WARPS;   // converter warps (TC_TMEM_A): one per TMEM lane quarter
-constexpr int TC_THREADS = 32 * (TC_CONV_WARP0 + (TC_TMEM_A ? 4 : 0));
+constexpr int TC_THREADS = 32 * (TC_DEC_FIRST + TC_NDEC_WARPS);
 constexpr int TC_LAUNCH_REGS = (65536 / TC_THREADS) & ~7;   // what __launch_bounds__(TC_THREADS, 1) lets ptxas give every thread
 template <int N> __device__ __forceinline__ void tc_reg_budget() {   // a role's setmaxnreg (whole warpgroup); 0 = keep the launch allocation
   if constexpr (N > TC_LAUNCH_REGS) ptx::reg_inc<N>();
   else if constexpr (N > 0 && N < TC_LAUNCH_REGS) ptx::reg_dec<N>();
 }
-// tensor memory: two accumulators of TC_D_COLS fp32 columns; with TC_TMEM_A also TC_NTA query-tile stages of 64 columns
+// tensor memory: TC_NACC accumulators of TC_D_COLS fp32 columns
 // (128 lanes x 128 fp16 = 64 packed 32-bit columns: lane = (query, token) row, column j = dims 2j, 2j+1)
-constexpr int TC_NACC_ = TC_TMEM_A ? 2 : TC_NACC;   // accumulators in use
-constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = TC_TMEM_A ? 192 : 512 / TC_NACC_, TC_A_COL0 = 2 * TC_D_COLS, TC_A_TCOLS = 64;
-constexpr int TC_NTA = 2;
+constexpr int TC_NACC_ = TC_NACC;
+constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 512 / TC_NACC_;
 
 // Measurement-only build (-DTC_PROF=1): every mbarrier wait is timed with clock64 and charged to (warp, wait tag); slot 0 of a
 // warp holds the clocks of its whole role loop.  Read back with cb_debug_tc_prof (tools/tc_wait_profile.py).
@@ -181,9 +175,7 @@ struct Barriers {
   uint64_t b_full[TC_NSLOT], b_empty[TC_NSLOT], meta_full[TC_NSLOT], meta_empty[TC_NSLOT];
   uint64_t a_full[TC_MAX_ASTAGES], a_empty[TC_MAX_ASTAGES];
   uint64_t d_full[TC_EPI_SETS][4], d_empty[4];
-  uint64_t at_full[TC_NTA], at_empty[TC_NTA];   // query-tile stages in tensor memory (TC_TMEM_A)
-  uint64_t l_afull[2][2], l_dempty[2], l_dfull[2];   // two-lane kernel: lane's A tile t holds a group / accumulator drained / MMAs retired
-  uint64_t t2_afull[2][TC_MAX_ASTAGES], t2_aempty[2][TC_MAX_ASTAGES];   // two-lane kernel: bulk-copy stage barriers PER LANE (see t2_loader_role)
+  uint64_t a_full2[2][TC_MAX_ASTAGES];   // TC_NISSUE == 2: "tile landed" barriers per (issuer, stage) (see tc_loader_role)
 };
 
 struct TcParams {
@@ -365,7 +357,7 @@ __device__ __forceinline__ void tc_fill_lut(uint8_t* s_lut, const float* __restr
 #define TC_DEC_PREFETCH 0              // (measured slower: 164.5 vs 162.0 ms at C, 101.2 vs 94.6 clustered; profiles/r02_ab_dec_prefetch.txt) 1 = decompression teams request the first codes of their next passage one passage ahead
 #endif
 #ifndef TC_DBATCH_
-#define TC_DBATCH_ 5
+#define TC_DBATCH_ ((TC_NISSUE == 2) ? 4 : 5)   // (the 704-thread build has 80 registers per thread: 5 spills)
 #endif
 constexpr int TC_DBATCH = TC_DBATCH_;   // decompression rounds whose loads are all in flight at once
 constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
@@ -441,7 +433,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 }
 
 // ---------------------------------------------------------------------------------------------
-// Roles shared by the scoring kernels (k_maxsim_tc and the two-lane k_maxsim_tc2)
+// Roles of the scoring kernel
 // ---------------------------------------------------------------------------------------------
 struct TcCtx {           // the CTA's shared-memory carve-up
   uint8_t* ring; uint8_t* a_tile0; Meta* meta; Barriers* bar; uint32_t* s_region; uint8_t* s_lut; int NA;
@@ -469,14 +461,14 @@ __device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S
     for (int g = 0; g < ngroups; g++) {
       const uint32_t st_g = st, par_g = a_par;
       if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
-      TCW(&bar->a_empty[st_g], par_g, 9);
+      TCW(&bar->a_empty[st_g], par_g, 9, TC_BACKOFF_NS);
       if (li == 0) TCT(6, gc);
       gc++;
       // With two issuers the "tile landed" barrier of a stage is the one of the group's ISSUER: a waiter must observe every phase
       // of a barrier it waits on, in order (an issuer asking for its group G while the stage's previous tile, the other issuer's
       // group G - NA, has not landed yet would take the phase of G - 2 NA -- same parity -- for its own).
 #if TC_NISSUE == 2
-      uint64_t* const full = &bar->t2_afull[turn][st_g];
+      uint64_t* const full = &bar->a_full2[turn][st_g];
       turn ^= 1u;
 #else
       uint64_t* const full = &bar->a_full[st_g];
@@ -544,7 +536,7 @@ __device__ __forceinline__ void tc_issuer_role(const TcCtx& S, const uint32_t tm
       if (++pq == period) { pq = 0; a_par ^= 1u; }
       if (!mine) { gc++; continue; }
       if (!waited) { TCW(&bar->b_full[slot], ph, 5); waited = true; }
-      TCW(&bar->t2_afull[me][st_g], par_g, 6);
+      TCW(&bar->a_full2[me][st_g], par_g, 6);
       TCT(0, gc);
       const uint32_t a_lo = a_lo0 + st_g * (uint32_t)(TC_A_BYTES >> 4);
       for (int c = 0; c < nchunk; c++) {
@@ -631,7 +623,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
 
     // meta slot: wait until entry e-4 has been fully consumed (that also frees its tile)
     const int slot = e & (TC_NSLOT - 1);
-    TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1);
+    TCW(&bar->meta_empty[slot], ((e >> TC_NSLOT_LOG2) & 1) ^ 1, 1, TC_BACKOFF_NS);
     TCE(7, e);
     if (tail < e - (TC_NSLOT - 1)) tail = e - (TC_NSLOT - 1);
     // ring region: first fit at head, else wrap to 0; wait for the live entries it overlaps.  The
@@ -649,7 +641,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
         if (off < s_region[2 * sj + 1] && s_region[2 * sj] < off + bytes && need < ej + 1) need = ej + 1;
       }
     }
-    for (; tail < need; tail++) TCW(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> TC_NSLOT_LOG2) & 1, 2);
+    for (; tail < need; tail++) TCW(&bar->b_empty[tail & (TC_NSLOT - 1)], (tail >> TC_NSLOT_LOG2) & 1, 2, TC_BACKOFF_NS);
     __syncwarp();
     if (lane == 0) { s_region[2 * slot] = off; s_region[2 * slot + 1] = off + bytes; }
     __syncwarp();
@@ -708,7 +700,7 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
     bool stop = false;
     for (int ee = (e >= TC_NTEAMS ? e - TC_NTEAMS + 1 : 0); ee <= e; ee++) {
       const int sl = ee & (TC_NSLOT - 1);
-      TCW(&bar->meta_full[sl], (ee >> TC_NSLOT_LOG2) & 1, 12, 20);
+      TCW(&bar->meta_full[sl], (ee >> TC_NSLOT_LOG2) & 1, 12, TC_BACKOFF_DEC_NS);
       if (meta[sl].ncand < 0) { stop = true; break; }
       if (ee != e) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[sl]); }
     }
@@ -773,15 +765,14 @@ k_maxsim_tc(TcParams P) {
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
       ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], TC_NISSUE);
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + (TC_TMEM_A ? 4 : 0) + ((TC_NISSUE == 2 && !(TC_NI_DBG & 1)) ? 2 : 0));
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + ((TC_NISSUE == 2 && !(TC_NI_DBG & 1)) ? 2 : 0));
     }
     for (int i = 0; i < TC_NACC_; i++) {
       for (int s = 0; s < TC_EPI_SETS; s++) ptx::mbar_init(&bar->d_full[s][i], 1);
       ptx::mbar_init(&bar->d_empty[i], 4);
     }
-    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], TC_TMEM_A ? 4 : 1); }
-    if (TC_NISSUE == 2) for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->t2_afull[0][i], TC_NLOAD); ptx::mbar_init(&bar->t2_afull[1][i], TC_NLOAD); }
-    for (int i = 0; i < TC_NTA; i++) { ptx::mbar_init(&bar->at_full[i], 4); ptx::mbar_init(&bar->at_empty[i], 1); }
+    for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full[i], TC_NLOAD); ptx::mbar_init(&bar->a_empty[i], 1); }
+    if (TC_NISSUE == 2) for (int i = 0; i < TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->a_full2[0][i], TC_NLOAD); ptx::mbar_init(&bar->a_full2[1][i], TC_NLOAD); }
     ptx::fence_barrier_init();
   }
   tc_fill_lut<NBITS>(s_lut, P.weights, tid, TC_THREADS);
@@ -834,13 +825,8 @@ k_maxsim_tc(TcParams P) {
         const int ngroups = (ncand + 3) >> 2;
         TCW(&bar->b_full[slot], ph, 5);
         for (int g = 0; g < ngroups; g++) {
-#if TC_TMEM_A
-          TCW(&bar->at_full[st], a_par, 6);                    // (st / a_par run over the TC_NTA tensor-memory stages here)
-          const uint32_t a_tmem = tmem_base + TC_A_COL0 + st * TC_A_TCOLS;
-#else
           TCW(&bar->a_full[st], a_par, 6);
           const uint32_t a_lo = a_lo0 + st * (uint32_t)(TC_A_BYTES >> 4);
-#endif
           TCT(0, gc);
           for (int c = 0; c < nchunk; c++) {
             TCW(&bar->d_empty[ds], d_par, 7);
@@ -853,18 +839,10 @@ k_maxsim_tc(TcParams P) {
 #pragma unroll
             for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
               const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
-#if TC_TMEM_A
-              ptx::mma_f16_ts(d_tmem, a_tmem + (uint32_t)k * 8u, db, idesc, k > 0 ? 1u : 0u);   // K = 16 step = 8 packed columns
-#else
               const uint64_t da = ((uint64_t)HI_A << 32) | (uint64_t)(a_lo + (uint32_t)((k >> 2) * 64 + (k & 3) * 2));
               ptx::mma_f16_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
-#endif
             }
-#if TC_TMEM_A
-            if (c == nchunk - 1) ptx::tc_commit(&bar->at_empty[st]);
-#else
             if (c == nchunk - 1) ptx::tc_commit(&bar->a_empty[st]);
-#endif
             ptx::tc_commit(&bar->d_full[eset][ds]);
             TCP_END(16);
             TCT(2, gc);
@@ -872,7 +850,7 @@ k_maxsim_tc(TcParams P) {
             d_par ^= (ds == 0u) ? 1u : 0u;
           }
           if (++eset == (uint32_t)TC_EPI_SETS) eset = 0;
-          if (++st == (uint32_t)(TC_TMEM_A ? TC_NTA : NA)) { st = 0; a_par ^= 1u; }
+          if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
           gc++;
         }
         ptx::tc_commit(&bar->b_empty[slot]);   // arrives after the passage's last MMA retires
@@ -941,7 +919,7 @@ k_maxsim_tc(TcParams P) {
 #endif
           const int ncol = (TC_ABLATE & 2) ? 16 : ((c > 0 && c == nchunk - 1) ? n1 : n0);
           const int nfull = ncol >> 5;           // full 32-column chunks (<= 7)
-          TCW(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11);
+          TCW(&bar->d_full[myset][ds], (fpar >> ds) & 1u, 11, TC_BACKOFF_EPI_NS);
           fpar ^= 1u << ds;
           ptx::tc_fence_after();
           if (warp == 4 || warp == 8) TCT(3, gc);
@@ -1035,67 +1013,6 @@ k_maxsim_tc(TcParams P) {
     }
     flush();
     flush();
-  } else if (TC_TMEM_A && warp >= TC_CONV_WARP0) {
-    // ===== converters (TC_TMEM_A): query tiles shared memory -> registers -> tensor memory.  Why: the tensor core
-    // fetches shared-memory operands at ~64 B/clk/SM (measured: every SS-mode MMA of this library takes
-    // (A bytes + B bytes) / 64 clocks -- 104 clocks for M = 128, N = 80 against 40 clocks of math), and the 4 KB A
-    // slice of every K-step is the bulk of it.  From tensor memory the A operand costs nothing, so the MMA of a
-    // group drops from ~830 to ~320 clocks.  The tiles still arrive by bulk copy (deep, latency-tolerant
-    // prefetch); warp j of this set owns TMEM lane quarter j = query j of the group: thread = one (query, token)
-    // row, which it reads out of the SWIZZLE_128B stage with sixteen conflict-free 16-byte loads (the 8 lanes
-    // of a quarter-warp sit on 8 different 16-byte bank groups by construction of the swizzle) and writes as
-    // the 64 packed columns of its lane with tcgen05.st. =====
-    tc_reg_budget<TC_REG_CONV>();
-    const int j = warp - TC_CONV_WARP0;
-    const uint32_t a_lane = tmem_base + TC_A_COL0 + ((uint32_t)(j * 32) << 16);
-    // row `lane` of query j inside a stage: 8-row group lane >> 3 (2048 B apart), row lane & 7 (128 B), K-block 1024 B apart
-    const uint32_t row_off = (uint32_t)j * TC_Q_BYTES + (uint32_t)(lane >> 3) * 2048u + (uint32_t)(lane & 7) * 128u;
-    const uint32_t r7 = (uint32_t)lane & 7u;
-    uint32_t st = 0, a_par = 0;      // shared-memory stage / parity of its next a_full phase
-    uint32_t ts = 0, t_par = 1;      // tensor-memory stage / parity of its next at_empty phase
-    [[maybe_unused]] int gc = 0;
-    for (int e = 0;; e++) {
-      const int slot = e & (TC_NSLOT - 1);
-      TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 13);
-      const int ncand = meta[slot].ncand;
-      if (ncand < 0) break;
-      const int ngroups = (ncand + 3) >> 2;
-      for (int g = 0; g < ngroups; g++) {
-        const bool have = (TC_ABLATE & 1) ? (j == 0) : (g * 4 + j < ncand);   // a short last group leaves the other quarters stale (never read out)
-        TCW(&bar->a_full[st], a_par, 14);
-        if (j == 0) TCT(7, gc);
-        uint32_t r[64];
-        TCP_BEGIN();
-        if (have) {
-          const uint8_t* src = a_tile0 + (size_t)st * TC_A_BYTES + row_off;
-#pragma unroll
-          for (int c = 0; c < 16; c++) {      // 16-byte chunk c & 7 of K-block c >> 3 sits at chunk (c & 7) ^ (row & 7)
-            const uint4 v = *reinterpret_cast<const uint4*>(src + (c >> 3) * 1024 + ((((uint32_t)c & 7u) ^ r7) << 4));
-            r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
-          }
-        }
-        TCW(&bar->at_empty[ts], t_par, 15);
-        ptx::tc_fence_after();
-        if (j == 0) TCT(8, gc);
-        if (have) {
-          ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS, r);
-          ptx::tmem_st_32x32b_x32(a_lane + ts * TC_A_TCOLS + 32, r + 32);
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->a_empty[st]);   // the shared-memory stage is free: its loads have landed (tcgen05.st took the registers)
-        if (have) ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->at_full[ts]);
-        TCP_END(18);
-        if (j == 0) TCT(9, gc);
-        gc++;
-        if (++st == (uint32_t)NA) { st = 0; a_par ^= 1u; }
-        if (++ts == (uint32_t)TC_NTA) { ts = 0; t_par ^= 1u; }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
-    }
   } else {
     tc_reg_budget<TC_REG_DEC>();
     if (warp < TC_XISS_WARP0) {
@@ -1131,417 +1048,6 @@ k_maxsim_tc(TcParams P) {
   }
 }
 
-
-// =============================================================================================
-// Two-lane scoring kernel (TC_LANES == 2).
-//
-// Why: the event trace of the one-lane kernel (tools/tc_trace.py, profiles/r02_wait_profile.txt) shows a group's life fully
-// serialised behind ONE thread: the MMA issuer needs ~850 clocks of its own instruction latency per 4-query group (two mbarrier
-// probes, ~50 uniform-datapath instructions of descriptor arithmetic, 8 tcgen05.mma + 2 commits) whatever the tensor pipe is
-// doing; the shared-memory-operand MMAs of a group occupy the tensor pipe for (4 KB A + 2.5 KB B) / 64 B/clk x 8 = ~830 clocks; and
-// one epilogue set needs ~750.  Three unrelated ~800-clock limits in a row: removing any one of them (two issuers; A in tensor
-// memory; two epilogue sets) alone changes nothing, which is what eleven A/B builds had measured.  This kernel removes all three:
-//   * groups alternate between two LANES; lane s = issuer warp s + worker set s (4 warps) + accumulator s + A-tile s in tensor memory;
-//   * the A operand is read from TENSOR MEMORY (tcgen05.mma [tmem], desc_b): a group's 8 MMAs take 8 x N/2 clocks of pure math;
-//   * a WORKER warp (one per TMEM lane quarter = one query of the group) is converter and epilogue in one: when the lane's MMAs
-//     retire it stores the NEXT group's query rows (already waiting in its registers) into the A tile with tcgen05.st, reads the
-//     accumulator (max over tokens), hands both back to the issuer with ONE barrier arrival, then sums / records the score and
-//     pulls the rows of the group after next out of the bulk-copy stage (conflict-free LDS of the swizzled tile).
-// Everything else (scheduler, loaders, decompression teams, pair-list output) is shared with k_maxsim_tc.
-//   * TWO A tiles per lane: the rows of the lane's group i+2 are stored (off the critical path, right after they were pulled out
-//     of the bulk-copy stage) into the tile group i used, whose MMAs have retired, while group i+1's MMAs run out of the other.
-// Tensor memory: lane s owns columns 256 s .. 256 s + 255: accumulator (128 columns: N <= 128 per chunk, up to 3 chunks per
-// passage) at +0, A tiles (64 packed columns each) at +128 and +192.
-// =============================================================================================
-constexpr int T2_NLOAD = 4;                         // loader warps 4..7
-constexpr int T2_WORK_WARP0 = 8, T2_DEC_WARP0 = 16; // workers 8..15 (set = (warp - 8) >> 2), decompression 16..23
-constexpr int T2_THREADS = 32 * 24;
-constexpr uint32_t T2_LANE_COLS = 256, T2_A_COL0 = 128, T2_A_TCOLS = 64;
-#ifndef T2_READ_MODE
-#define T2_READ_MODE 0
-#endif
-#ifndef T2_REG_CTRL
-#define T2_REG_CTRL 48
-#define T2_REG_LOAD 32
-#define T2_REG_WORK 104
-#define T2_REG_DEC 96
-#endif
-template <int N> __device__ __forceinline__ void t2_reg_budget() {   // 768 threads: launch allocation 80
-  if constexpr (N > 80) ptx::reg_inc<N>();
-  else if constexpr (N > 0 && N < 80) ptx::reg_dec<N>();
-}
-
-// Position in the CTA's stream of groups: passage entry e, group g of its ng, global group index G (lane = G & 1) and the
-// bulk-copy stage / phase parity of group G.  `pending`: entry e has not been read yet (it may not be published yet).
-struct T2Cursor {
-  int e, g, ng, ncand; uint32_t G, st, q, par; bool pending, end;   // q = G % period, par = (G / period) & 1 (period: t2_loader_role)
-};
-
-// Query-tile loaders of the two-lane kernel.  Group G lands in stage G % NA as in k_maxsim_tc, but its full / empty barriers are
-// the ones of its LANE (G & 1): a barrier phase must be observed by every party that waits on the barrier, in order -- a lane's
-// workers never look at the other lane's groups, and with one barrier per stage a worker asking for group G while the stage
-// still waits for group G - NA (the other lane's) would see the phase of G - 2 NA, same parity, as complete.  Barrier
-// (lane, stage) serves every `period`-th group, period = lcm(2, NA): phase of group G = G / period.
-template <int NLOAD>
-__device__ __forceinline__ void t2_loader_role(const TcParams& P, const TcCtx& S, const int li, const int warp, const int lane) {
-  Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const a_tile0 = S.a_tile0;
-  const uint32_t NA = (uint32_t)S.NA, period = (NA & 1u) ? 2u * NA : NA;
-  (void)warp;
-  uint32_t G = 0, st = 0;        // group counter / its stage
-  uint32_t pq = 0, pph = 0;      // (G - NA) % period and the phase parity of group G - NA, the stage's previous user
-  for (int e = 0;; e++) {
-    const int slot = e & (TC_NSLOT - 1);
-    TCW(&bar->meta_full[slot], (e >> TC_NSLOT_LOG2) & 1, 8);
-    const Meta& m = meta[slot];
-    const int ncand = m.ncand;
-    if (ncand < 0) break;
-    const int ngroups = (ncand + 3) >> 2;
-    for (int g = 0; g < ngroups; g++) {
-      if (G >= NA) {
-        TCW(&bar->t2_aempty[(G - NA) & 1u][st], pph, 9);
-        if (++pq == period) { pq = 0; pph ^= 1u; }
-      }
-      if (li == 0 && (G & 1u) == 0) TCT(6, (int)(G >> 1));
-      uint64_t* const full = &bar->t2_afull[G & 1u][st];
-      uint8_t* dst = a_tile0 + (size_t)st * TC_A_BYTES;
-      G++;
-      if (++st == NA) st = 0;
-      const int nqg = (TC_ABLATE & 1) ? 1 : min(4, ncand - g * 4);
-      const int nmine = (nqg - li + NLOAD - 1) / NLOAD;      // queries li, li + NLOAD, ... < nqg
-      if (nmine <= 0) {
-        if (ptx::elect_one()) ptx::mbar_arrive(full);
-        continue;
-      }
-      const int qv = (lane < nmine) ? (int)m.q[g * 4 + li + lane * NLOAD] : 0;   // lane i holds this loader's i-th query
-      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full, (uint32_t)nmine * TC_Q_BYTES);
-      for (int i = 0; i < nmine; i++) {
-        const int q = __shfl_sync(0xffffffffu, qv, i);
-        if (ptx::elect_one())
-          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[slot]);
-  }
-}
-
-template <int NBITS>
-__global__ void __launch_bounds__(T2_THREADS, 1)
-k_maxsim_tc2(TcParams P) {
-  if (*P.q_flag != 0) return;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int NA = P.nastages;
-  uint8_t* ring = smem;
-  uint8_t* a_tile0 = smem + P.ring_bytes;
-  Meta* meta = reinterpret_cast<Meta*>(a_tile0 + (size_t)NA * TC_A_BYTES);
-  Barriers* bar = reinterpret_cast<Barriers*>(meta + TC_NSLOT);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
-  uint32_t* s_region = s_tmem + 4;
-  uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_region + 2 * TC_NSLOT) + 64;
-  s_lut += (128u - (ptx::smem_u32(s_lut) & 127u)) & 127u;
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-#if TC_PROF
-  for (int i = tid; i < 32 * 24; i += T2_THREADS) s_prof[i] = 0;
-  const long long prof_t0 = clock64();
-#endif
-  if (tid == 0) {
-    for (int i = 0; i < TC_NSLOT; i++) {
-      ptx::mbar_init(&bar->b_full[i], TC_TEAM_WARPS); ptx::mbar_init(&bar->b_empty[i], 2);          // both issuers commit
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], T2_NLOAD + 8 + TC_NDEC_WARPS + 2);
-    }
-    for (int i = 0; i < 2 * TC_MAX_ASTAGES; i++) { ptx::mbar_init(&bar->t2_afull[0][i], T2_NLOAD); ptx::mbar_init(&bar->t2_aempty[0][i], 4); }
-    for (int i = 0; i < 2; i++) {
-      ptx::mbar_init(&bar->l_afull[i][0], 4); ptx::mbar_init(&bar->l_afull[i][1], 4);
-      ptx::mbar_init(&bar->l_dempty[i], 4);   ptx::mbar_init(&bar->l_dfull[i], 1);
-    }
-    ptx::fence_barrier_init();
-  }
-  tc_fill_lut<NBITS>(s_lut, P.weights, tid, T2_THREADS);
-  if (warp == 1) ptx::tmem_alloc(s_tmem, TC_TMEM_COLS);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-  const TcCtx S{ring, a_tile0, meta, bar, s_region, s_lut, NA};
-  const uint32_t period = (NA & 1) ? 2u * (uint32_t)NA : (uint32_t)NA;   // groups between two uses of a (lane, stage) barrier
-
-  // Cursor over the stream of groups.  cur_seek(c, s, blocking, release) moves c to the next group of lane s at or after its
-  // position (or to the end of the stream); with blocking = false it gives up -- returns false, resumable -- as soon as it would
-  // need a passage entry the scheduler has not published yet.  cur_skip steps past the group c is on.  `release`: this walker is
-  // one of the arrivals that free a passage's meta slot when it leaves the passage.
-  // non-blocking probe of a barrier phase with ONE answer for the whole warp: the lanes of a warp can see a phase complete at
-  // different instants, and a warp split on the answer would run .sync.aligned tensor-memory instructions with a partial mask
-  auto probe = [&](uint64_t* b, uint32_t parity) __attribute__((always_inline)) -> bool {
-    return __shfl_sync(0xffffffffu, ptx::mbar_test_wait(b, parity) ? 1 : 0, 0) != 0;
-  };
-  auto cur_start = [&](T2Cursor& c) __attribute__((always_inline)) {
-    c.e = 0; c.g = 0; c.ng = 0; c.ncand = 0; c.G = 0; c.st = 0; c.q = 0; c.par = 0; c.pending = true; c.end = false;
-  };
-  auto cur_skip = [&](T2Cursor& c, bool release) __attribute__((always_inline)) {
-    c.G++;
-    if (++c.st == (uint32_t)NA) c.st = 0;
-    if (++c.q == period) { c.q = 0; c.par ^= 1u; }
-    if (++c.g < c.ng) return;
-    if (release) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar->meta_empty[c.e & (TC_NSLOT - 1)]); }
-    c.e++;
-    c.pending = true;
-  };
-  auto cur_seek = [&](T2Cursor& c, uint32_t s, bool blocking, bool release, int tag) __attribute__((always_inline)) -> bool {
-    while (true) {
-      if (c.pending) {
-        const int slot = c.e & (TC_NSLOT - 1);
-        const uint32_t ph = (c.e >> TC_NSLOT_LOG2) & 1;
-        if (blocking) TCW(&bar->meta_full[slot], ph, tag);
-        else if (!probe(&bar->meta_full[slot], ph)) return false;
-        c.ncand = meta[slot].ncand;
-        c.end = c.ncand < 0;
-        c.ng = (c.ncand + 3) >> 2;
-        c.g = 0;
-        c.pending = false;
-      }
-      if (c.end || (c.G & 1u) == s) return true;
-      cur_skip(c, release);
-    }
-  };
-
-  if (warp < 4) {
-    t2_reg_budget<T2_REG_CTRL>();
-    if (warp == 0) {
-      tc_scheduler_role(P, S, warp, lane);
-    } else if (warp <= 2) {
-      // ===== MMA issuer of lane s: ONE elected thread; walks every passage (it is one of the arrivals that free the passage's
-      // operand tile and meta slot) and issues the groups with G & 1 == s =====
-      const uint32_t s = (uint32_t)(warp - 1);
-      if (ptx::elect_one()) {
-        const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3ffffu) >> 4) | (1u << 16);
-        constexpr uint32_t HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t d_tmem = tmem_base + s * T2_LANE_COLS, a_tmem0 = d_tmem + T2_A_COL0;
-        uint32_t dpar = 1;                 // parity of the lane's next l_dempty phase (the accumulator starts out free)
-        uint32_t own = 0;                  // own groups issued: A tile = own & 1, phase parity of its l_afull = (own >> 1) & 1
-        [[maybe_unused]] int gc = 0;
-        T2Cursor c;
-        cur_start(c);
-        int e_cur = -1;
-        int nchunk = 1, n0 = 16, n1 = 0;
-        uint32_t b_lo0 = 0, kb0 = 0, kb1 = 0, idesc0 = 0, idesc1 = 0;
-        while (true) {
-          // every group of the stream, in order (blocking); a passage is left -- b_empty / meta_empty -- when its last group is passed
-          if (c.pending) {
-            const int slot = c.e & (TC_NSLOT - 1);
-            TCW(&bar->meta_full[slot], (c.e >> TC_NSLOT_LOG2) & 1, 4);
-            c.ncand = meta[slot].ncand;
-            c.end = c.ncand < 0;
-            c.ng = (c.ncand + 3) >> 2;
-            c.g = 0;
-            c.pending = false;
-          }
-          if (c.end) break;
-          const int slot = c.e & (TC_NSLOT - 1);
-          if ((c.G & 1u) == s) {
-            if (e_cur != c.e) {              // first own group in this passage: its geometry, and its operand tile must be complete
-              e_cur = c.e;
-              nchunk = meta[slot].nchunk; n0 = meta[slot].n0; n1 = meta[slot].n1;
-              b_lo0 = ring_lo + (meta[slot].b_off >> 4);
-              kb0 = (uint32_t)n0 * 8u; kb1 = (uint32_t)n1 * 8u;
-              idesc0 = ptx::idesc_f16(128, n0, 0); idesc1 = ptx::idesc_f16(128, n1 > 0 ? n1 : 16, 0);
-              TCW(&bar->b_full[slot], (c.e >> TC_NSLOT_LOG2) & 1, 5);
-            }
-            const uint32_t tile = own & 1u;
-            TCW(&bar->l_afull[s][tile], (own >> 1) & 1u, 6);
-            if (s == 0) TCT(0, gc);
-            own++;
-            const uint32_t a_tmem = a_tmem0 + tile * T2_A_TCOLS;
-            for (int ch = 0; ch < nchunk; ch++) {
-              TCW(&bar->l_dempty[s], dpar, 7);
-              dpar ^= 1u;
-              ptx::tc_fence_after();
-              if (s == 0 && ch == 0) TCT(1, gc);
-              const bool lastc = (nchunk > 1) && (ch == nchunk - 1);
-              const uint32_t b_lo = b_lo0 + (uint32_t)(ch * n0) * 16u, kb = lastc ? kb1 : kb0, idesc = lastc ? idesc1 : idesc0;
-              TCP_BEGIN();
-#pragma unroll
-              for (int k = 0; k < ((TC_ABLATE & 8) ? 2 : 8); k++) {
-                const uint64_t db = ((uint64_t)HI_B << 32) | (uint64_t)(b_lo + (uint32_t)(k >> 2) * kb + (uint32_t)(k & 3) * 2);
-                ptx::mma_f16_ts(d_tmem, a_tmem + (uint32_t)k * 8u, db, idesc, k > 0 ? 1u : 0u);
-              }
-              ptx::tc_commit(&bar->l_dfull[s]);
-              TCP_END(16);
-              if (s == 0) TCT(2, gc);
-            }
-            gc++;
-          }
-          // leaving the passage: this issuer's MMAs on its tile have been issued -> b_empty arrives when they retire
-          if (c.g + 1 >= c.ng) { ptx::tc_commit(&bar->b_empty[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
-          cur_skip(c, false);
-        }
-      }
-      __syncwarp();
-    }
-  } else if (warp < T2_WORK_WARP0) {
-    t2_reg_budget<T2_REG_LOAD>();
-    t2_loader_role<T2_NLOAD>(P, S, warp - 4, warp, lane);
-  } else if (warp < T2_DEC_WARP0) {
-    t2_reg_budget<T2_REG_WORK>();
-    // ===== worker of lane s, TMEM lane quarter q4 (= query slot q4 of every group of the lane) =====
-    const int q4 = warp & 3;
-    const uint32_t s = (uint32_t)(warp - T2_WORK_WARP0) >> 2;
-    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    const uint32_t d_addr = tmem_base + s * T2_LANE_COLS + lane_off, a_addr0 = d_addr + T2_A_COL0;
-    // row `lane` of query q4 inside a bulk-copy stage (converter geometry of k_maxsim_tc)
-    const uint32_t row_off = (uint32_t)q4 * TC_Q_BYTES + (uint32_t)(lane >> 3) * 2048u + (uint32_t)(lane & 7) * 128u;
-    const uint32_t r7 = (uint32_t)lane & 7u;
-    uint32_t dpar = 0;                       // parity of the lane's next l_dfull phase
-    int cnt = 0, my_q = 0;
-    uint64_t my_key = 0;
-    bool pend = false;
-    uint64_t pend_key = 0;
-    uint64_t* pend_ptr = nullptr;
-    int pend_pos = 0;
-    auto flush = [&]() __attribute__((always_inline)) {
-      if (pend) pend_ptr[pend_pos] = pend_key;
-      pend = lane < cnt;
-      if (pend) {
-        pend_ptr = P.pairs + P.list_off[my_q];
-        pend_pos = atomicAdd(&P.cursors[my_q], 1);
-        pend_key = my_key;
-      }
-      cnt = 0;
-    };
-    // Query rows of group `c` : bulk-copy stage -> registers -> A tile `tile` of the lane (all four quarters do it whether or not
-    // the group has a query in their slot: a stale row only produces an accumulator row nobody reads); the stage goes back to the
-    // loaders, the tile is handed to the issuer.
-    uint32_t conv = 0, done = 0;            // own groups converted / scored
-    auto convert = [&](const T2Cursor& c, uint32_t tile) __attribute__((always_inline)) {
-      uint32_t r[64];                         // this thread's (query, token) row: 128 fp16 = 64 packed columns
-      if (warp == T2_WORK_WARP0) TCT(7, (int)conv);
-      TCW(&bar->t2_afull[s][c.st], c.par, 14);
-      const uint8_t* src = a_tile0 + (size_t)c.st * TC_A_BYTES + row_off;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + (i >> 3) * 1024 + ((((uint32_t)i & 7u) ^ r7) << 4));
-        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->t2_aempty[s][c.st]);
-      if (warp == T2_WORK_WARP0) TCT(8, (int)conv);
-      const uint32_t a_addr = a_addr0 + tile * T2_A_TCOLS;
-      ptx::tmem_st_32x32b_x32(a_addr, r);
-      ptx::tmem_st_32x32b_x32(a_addr + 32, r + 32);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->l_afull[s][tile]);
-      if (warp == T2_WORK_WARP0) TCT(9, (int)conv);
-    };
-    // max over one chunk's accumulator columns
-    auto read_chunk = [&](int ncol, float& m0, float& m1, float& m2, float& m3) __attribute__((always_inline)) {
-#if T2_READ_MODE == 0
-      // one 32-column piece at a time (fewest registers)
-      const int nfull = ncol >> 5;
-      uint32_t ra[32];
-#pragma unroll 1
-      for (int p = 0; p < nfull; p++) {
-        ptx::tmem_ld_32x32b_x32(d_addr + p * 32, ra);
-        ptx::tmem_ld_wait();
-        fold32(ra, m0, m1, m2, m3);
-      }
-      if (ncol & 16) {
-        uint32_t rt[16];
-        ptx::tmem_ld_32x32b_x16(d_addr + nfull * 32, rt);
-        ptx::tmem_ld_wait();
-        fold16(rt, m0, m1, m2, m3);
-      }
-#else
-      // pieces of 32 columns (+ a 16-column tail), the load of the next piece in flight while the current one is folded
-      const int nfull = ncol >> 5, np = nfull + ((ncol >> 4) & 1);
-      uint32_t ra[32], rb[32];
-      if (nfull > 0) ptx::tmem_ld_32x32b_x32(d_addr, ra); else ptx::tmem_ld_32x32b_x16_lo(d_addr, ra);
-      ptx::tmem_ld_wait();
-      for (int p = 0; p < np; p += 2) {
-        if (p + 1 < np) { if (p + 1 < nfull) ptx::tmem_ld_32x32b_x32(d_addr + (p + 1) * 32, rb); else ptx::tmem_ld_32x32b_x16_lo(d_addr + (p + 1) * 32, rb); }
-        if (p < nfull) fold32(ra, m0, m1, m2, m3); else fold16_lo(ra, m0, m1, m2, m3);
-        if (p + 1 >= np) break;
-        ptx::tmem_ld_wait();
-        if (p + 2 < np) { if (p + 2 < nfull) ptx::tmem_ld_32x32b_x32(d_addr + (p + 2) * 32, ra); else ptx::tmem_ld_32x32b_x16_lo(d_addr + (p + 2) * 32, ra); }
-        if (p + 1 < nfull) fold32(rb, m0, m1, m2, m3); else fold16_lo(rb, m0, m1, m2, m3);
-        if (p + 2 < np) ptx::tmem_ld_wait();
-      }
-#endif
-    };
-    // Epilogue cursor ec (blocking; releases passages) and converter cursor cc (the next group to convert; up to two own groups
-    // ahead of ec).  The converter only BLOCKS -- on a passage entry or a query tile -- when the lane has nothing in flight
-    // (conv == done: the group it needs is the one ec stands on, whose passage is already published); otherwise it converts
-    // opportunistically, so a warp never waits for a future passage while it still holds what that passage's ring space
-    // depends on.
-    T2Cursor ec, cc;
-    cur_start(ec);
-    cur_seek(ec, s, true, true, 10);
-    cc = ec;
-    bool cc_end = false;
-    [[maybe_unused]] int gc = 0;
-    while (!ec.end) {
-      while (conv - done < 2u && !cc_end) {
-        const bool blocking = (conv == done);
-        if (!cur_seek(cc, s, blocking, false, 13)) break;
-        if (cc.end) { cc_end = true; break; }
-        if (!blocking && !probe(&bar->t2_afull[s][cc.st], cc.par)) break;
-        convert(cc, conv & 1u);
-        conv++;
-        cur_skip(cc, false);
-      }
-      const int slot = ec.e & (TC_NSLOT - 1);
-      const Meta& m = meta[slot];
-      const int nchunk = m.nchunk;
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      for (int ch = 0; ch < nchunk; ch++) {
-        TCW(&bar->l_dfull[s], dpar, 11);
-        dpar ^= 1u;
-        ptx::tc_fence_after();
-        if (warp == T2_WORK_WARP0 && ch == 0) TCT(3, gc);
-        read_chunk((TC_ABLATE & 2) ? 16 : ((nchunk > 1 && ch == nchunk - 1) ? m.n1 : m.n0), m0, m1, m2, m3);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->l_dempty[s]);   // accumulator drained
-      }
-      if (warp == T2_WORK_WARP0) TCT(4, gc);
-      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      const int isum = __reduce_add_sync(0xffffffffu, __float2int_rn(mx * 262144.0f));   // exact 2^-18 fixed-point sum (k_maxsim_tc)
-      const int qi = ec.g * 4 + q4;
-      if (qi < ec.ncand) {
-        const float score = (float)isum * (1.0f / 262144.0f);
-        if (lane == (cnt & 31)) {
-          my_q = m.q[qi];
-          my_key = ((uint64_t)cb_orderable(score) << 32) | (0xffffffffu - (uint32_t)m.pid);
-        }
-        if (++cnt == 32) flush();
-      }
-      if (warp == T2_WORK_WARP0) TCT(5, gc);
-      gc++;
-      done++;
-      cur_skip(ec, true);
-      cur_seek(ec, s, true, true, 10);
-    }
-    flush();
-    flush();
-  } else {
-    t2_reg_budget<T2_REG_DEC>();
-    tc_decompress_role<NBITS>(P, S, (warp - T2_DEC_WARP0) / TC_TEAM_WARPS, (warp - T2_DEC_WARP0) % TC_TEAM_WARPS, warp, lane);
-  }
-
-#if TC_PROF
-  if (lane == 0) s_prof[warp * 24] = (unsigned long long)(clock64() - prof_t0);
-#endif
-  ptx::tc_fence_before();
-  __syncthreads();
-#if TC_PROF
-  for (int i = tid; i < 32 * 24; i += T2_THREADS) g_tc_prof[(size_t)blockIdx.x * 32 * 24 + i] = s_prof[i];
-#endif
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
-  }
-}
 
 // Parity hook (cb_debug_tc_operand): the decompression of the scoring kernel -- the SAME device functions,
 // one team of TC_TEAM_WARPS warps per listed passage -- with the operand tile copied out un-swizzled.
@@ -1641,13 +1147,8 @@ int32_t cb_stage34_tc(cb_index* ix, const float* dQ, int nq, int T, int W, const
   int64_t grid = ix->sm_count;
   const int64_t n_items = P.pid_list ? P.n_list : ix->Np;
   if (grid > n_items) grid = n_items;
-#if TC_LANES == 2
-#define CB_TC_KERNEL k_maxsim_tc2
-#define CB_TC_NTHREADS T2_THREADS
-#else
 #define CB_TC_KERNEL k_maxsim_tc
 #define CB_TC_NTHREADS TC_THREADS
-#endif
 #define CB_TC_LAUNCH(NB)                                                                                         \
   do {                                                                                                           \
     CB_CUDA(cudaFuncSetAttribute(CB_TC_KERNEL<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
