@@ -100,6 +100,20 @@ class ShardedSearcher:
         L.check(L.load().cb_merge_topk_device(self.searcher.device, n, nq, k, all_p.data_ptr(), all_s.data_ptr(),
                                               out_p.data_ptr(), out_s.data_ptr(), stream))
 
+    def probe_and_gather(self, Qd, stream=None):
+        """Stage 1 split by query: this rank probes queries [rank * per, (rank + 1) * per) and the ranks all-gather the
+        cells (int32 [world * per][T][nprobe], 1-based); every rank returns all rows."""
+        import torch
+        nq, T, _ = Qd.shape
+        nprobe = self.searcher.config.nprobe
+        lo, hi, per = query_slice(nq, self.world, self.rank)
+        if self._cells is None or tuple(self._cells.shape) != (self.world * per, T, nprobe):
+            self._cells = torch.zeros((self.world * per, T, nprobe), dtype=torch.int32, device=Qd.device)
+        if hi > lo:
+            self.searcher.probe_device(Qd[lo:hi].data_ptr(), hi - lo, T, self._cells[lo:hi].data_ptr(), stream=stream)
+        gather_cells(self._cells, per, self.rank, self.group)
+        return self._cells
+
     def search_batch_device(self, Qd, k, out_p, out_s, out_c, stream=None, local_p=None, local_s=None, plaid=None):
         """Qd float32 [nq][T][dim] on this rank's GPU (identical on every rank); out_p / out_s
         [nq][k] receive the GLOBAL first-k on every rank; out_c [nq] the local candidate counts.
@@ -114,14 +128,8 @@ class ShardedSearcher:
         def local(p, s_):
             if plaid is None and self.world > 1 and self.shard_stage1:
                 # stage 1 split by query: probe my slice, all-gather the cells, search with the cells given
-                nprobe = self.searcher.config.nprobe
-                lo, hi, per = query_slice(nq, self.world, self.rank)
-                if self._cells is None or tuple(self._cells.shape) != (self.world * per, T, nprobe):
-                    self._cells = torch.zeros((self.world * per, T, nprobe), dtype=torch.int32, device=Qd.device)
-                if hi > lo:
-                    self.searcher.probe_device(Qd[lo:hi].data_ptr(), hi - lo, T, self._cells[lo:hi].data_ptr(), stream=stream)
-                gather_cells(self._cells, per, self.rank, self.group)
-                self.searcher.search_batch_cells_device(Qd.data_ptr(), self._cells.data_ptr(), nq, T, k, p.data_ptr(),
+                cells = self.probe_and_gather(Qd, stream)
+                self.searcher.search_batch_cells_device(Qd.data_ptr(), cells.data_ptr(), nq, T, k, p.data_ptr(),
                                                         s_.data_ptr(), out_c.data_ptr(), stream=stream)
             elif plaid is None:
                 self.searcher.search_batch_device(Qd.data_ptr(), nq, T, k, p.data_ptr(), s_.data_ptr(), out_c.data_ptr(),
