@@ -329,6 +329,32 @@ def test_edge_cases_empty_and_ragged():
         assert c.tolist() == [0] * 5 and np.all(p == 0)
 
 
+@pytest.mark.parametrize("n_passages,n_queries,doclen_mean,doclen_std,K", [
+    (3000, 16, 40, 15, 256),     # every query a candidate of every passage: 4 full groups per passage, short MMAs (N = 48)
+    (3000, 23, 30, 20, 256),     # ragged last groups (23 candidates = 5 full groups + 3)
+    (1500, 9, 300, 60, 128),     # passages over 240 tokens: two accumulator passes per group
+])
+def test_two_issuer_pipeline_equals_generic_kernel(n_passages, n_queries, doclen_mean, doclen_std, K):
+    """The tcgen05 scoring kernel issues alternate 4-query groups from two threads.  Its first version shared one
+    "tile landed" barrier per query-tile stage between them; on exactly these shapes (many groups per passage, short
+    passages, few passages per CTA) an issuer took an old phase of the barrier for its own and the kernel died with a
+    launch failure.  The fused kernel must return what the generic fp32 kernel returns (final scores are exact fp32
+    re-scores in both: bit-identical)."""
+    ix = S.make_index(n_passages, K, seed=31, doclen_mean=doclen_mean, doclen_std=doclen_std)
+    Q = S.make_queries(ix["centroids"], n_queries, seed=32)
+    Qj = np.transpose(Q, (2, 1, 0))
+    with make_searcher(ix) as s:
+        for _ in range(3):                                           # timing-dependent: a few runs
+            p1, s1, c1 = s.search_batch(Qj, 10)
+        assert s.stat("tc_pairs") > 0
+        s.set_option("force_generic", 1)
+        p2, s2, c2 = s.search_batch(Qj, 10)
+    assert np.array_equal(c1, c2)
+    assert np.array_equal(p1, p2)
+    np.testing.assert_array_equal(s1, s2)
+
+
+
 def test_ivf_built_on_device_equals_given_ivf(tiny):
     ix, Q, oix = tiny
     no_ivf = dict(ix, ivf=None, ivf_lengths=None)
