@@ -657,7 +657,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         prof = dict(zip(sorted(prof), [float(x) for x in tt.tolist()]))
     roofline = leg.roofline(prof, pairs, pair_embs, args.workload)
-    roofline["scope"] = "this rank's shard (stage times = max over ranks)" if world > 1 else "the whole index"
+    roofline["scope"] = ("this rank's shard (stage times = max over ranks; ms_stage1 = stage 1 on the rank's query slice + the all-gather of the cells, "
+                         "which also absorbs the skew between the ranks' previous steps)") if world > 1 else "the whole index"
 
     # ---- parity at every N: all-query gate on every rank, result digest against the committed N = 1 digest
     parity = {"digest": result_digest, "tolerance": 1e-3, "stage1_rows_redone_by_exact_scan": flagged, "rescore_unsafe_queries": unsafe,
