@@ -50,9 +50,6 @@ namespace {
 #ifndef TC_BACKOFF_DEC_NS
 #define TC_BACKOFF_DEC_NS 20           // ... of the decompression warps' wait for the next passage
 #endif
-#ifndef TC_NI_DBG
-#define TC_NI_DBG 0                    // debugging switches of the two-issuer path
-#endif
 #ifndef TC_NISSUE
 #define TC_NISSUE 2                    // MMA issuer threads: 2 = two warps issue alternate groups, each into its own accumulator(s) (see tc_issuer_role)
 #endif
@@ -209,17 +206,6 @@ __device__ __forceinline__ void fold16(const uint32_t (&r)[16], float& m0, float
   m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
 }
 
-__device__ __forceinline__ void fold16_lo(const uint32_t (&r)[32], float& m0, float& m1, float& m2, float& m3) {
-  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])));
-  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
-  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])));
-  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
-  m0 = fmaxf(m0, fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])));
-  m1 = fmaxf(m1, fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
-  m2 = fmaxf(m2, fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])));
-  m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
-}
-
 // Decompression helpers.  EIGHT lanes expand one token (a warp expands 4 tokens at a time): lane l8
 // owns dims 8*l8 .. 8*l8+7 and 64+8*l8 .. 64+8*l8+7, i.e. 16-byte chunk l8 of BOTH 64-element
 // K-blocks of the fp16 operand row.  With that split (a) each of the lane's two 16-byte stores is,
@@ -353,9 +339,6 @@ __device__ __forceinline__ void tc_fill_lut(uint8_t* s_lut, const float* __restr
   }
 }
 
-#ifndef TC_DEC_PREFETCH
-#define TC_DEC_PREFETCH 0              // (measured slower: 164.5 vs 162.0 ms at C, 101.2 vs 94.6 clustered; profiles/r02_ab_dec_prefetch.txt) 1 = decompression teams request the first codes of their next passage one passage ahead
-#endif
 #ifndef TC_DBATCH_
 #define TC_DBATCH_ ((TC_NISSUE == 2) ? 4 : 5)   // (the 704-thread build has 80 registers per thread: 5 spills)
 #endif
@@ -365,27 +348,9 @@ constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
 // One team warp's share of a passage: packed codes/residuals -> normalised fp16 operand tile(s) in shared
 // memory (rows past the last token re-expand the last token).  Used by the scoring kernel's
 // decompression role and, unchanged, by the parity hook kernel k_tc_dump (DUMP = true).
-// codes of a team warp's FIRST batch of rounds of a passage (the loads the rest of the passage's loads depend on)
-__device__ __forceinline__ void tc_first_codes(const TcParams& P, int dw, int lane, int L, int nchunk, int n0, int n1, int64_t e0,
-                                               int32_t (&code)[TC_DBATCH]) {
-  constexpr int TEAM_WARPS = TC_TEAM_WARPS;
-  const int nrows = tc_total_rows(nchunk, n0, n1);
-  const int rr0 = 4 * dw + (lane >> 3);
-  const int nround = (nrows - 4 * dw + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);
-  const int nround_max = (nrows + 4 * TEAM_WARPS - 1) / (4 * TEAM_WARPS);
-  const int nbatch = (nround_max + TC_DBATCH - 1) / TC_DBATCH;
-  const int per = (nround_max + nbatch - 1) / nbatch;
-#pragma unroll
-  for (int i = 0; i < TC_DBATCH; i++) {
-    const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
-    code[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
-  }
-}
-
 template <int NBITS, bool DUMP>
 __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const uint8_t* __restrict__ lut_lane, int dw, int lane,
-                                                      int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out,
-                                                      bool have_first, const int32_t (&first)[TC_DBATCH]) {
+                                                      int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out) {
   constexpr int TEAM_WARPS = TC_TEAM_WARPS;
   const int l8 = lane & 7;
   const int nrows = tc_total_rows(nchunk, n0, n1);              // operand rows (multiple of 16)
@@ -396,11 +361,10 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
   const int nbatch = (nround_max + TC_DBATCH - 1) / TC_DBATCH;
   const int per = (nround_max + nbatch - 1) / nbatch;           // balanced batch length (<= TC_DBATCH)
   int32_t code_next[TC_DBATCH];
-  if (have_first) {                                             // requested while the team's previous passage was being expanded
 #pragma unroll
-    for (int i = 0; i < TC_DBATCH; i++) code_next[i] = first[i];
-  } else {
-    tc_first_codes(P, dw, lane, L, nchunk, n0, n1, e0, code_next);
+  for (int i = 0; i < TC_DBATCH; i++) {
+    const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
+    code_next[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
   }
   for (int j0 = 0; j0 < nround; j0 += per) {
     Bits16<NBITS> bits[TC_DBATCH];
@@ -560,9 +524,8 @@ __device__ __forceinline__ void tc_issuer_role(const TcCtx& S, const uint32_t tm
       }
       gc++;
     }
-    if ((TC_NI_DBG & 2) && !waited) ptx::mbar_arrive(&bar->b_empty[slot]);
-    else ptx::tc_commit(&bar->b_empty[slot]);   // arrives after this thread's earlier MMAs have retired (none of them may have read this tile)
-    if (!(TC_NI_DBG & 1)) ptx::mbar_arrive(&bar->meta_empty[slot]);
+    ptx::tc_commit(&bar->b_empty[slot]);   // arrives after this thread's earlier MMAs have retired (none of them may have read this tile)
+    ptx::mbar_arrive(&bar->meta_empty[slot]);
   }
 }
 
@@ -688,10 +651,6 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
   Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const ring = S.ring; uint8_t* const s_lut = S.s_lut;
   (void)warp;
   const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
-  bool have_first = false;                 // first_codes holds the first codes of the passage about to be expanded
-  int32_t first_codes[TC_DBATCH];
-#pragma unroll
-  for (int i = 0; i < TC_DBATCH; i++) first_codes[i] = 0;
   for (int e = team;; e += TC_NTEAMS) {
     // An entry of another team between this team's previous entry and e may end the stream.  Every
     // decompression warp looks at EVERY entry exactly once and is one of the arrivals that release
@@ -708,27 +667,9 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
     const int slot = e & (TC_NSLOT - 1);
     const Meta& m = meta[slot];
     if (dw == 0) TCE(9, e);
-    // The first codes of the team's NEXT passage are requested now, if the scheduler has already published it (the usual case:
-    // it runs up to TC_NSLOT entries ahead), so that one of the two dependent global round trips of a passage (codes -> centroid
-    // rows) overlaps the expansion of this one.  The peek does not consume the entry: the probe loop above still does.
-    bool have_next = false;
-    int32_t next_codes[TC_DBATCH];
-    if (TC_DEC_PREFETCH) {
-      const int en = e + TC_NTEAMS, sn = en & (TC_NSLOT - 1);
-      if (__shfl_sync(0xffffffffu, ptx::mbar_test_wait(&bar->meta_full[sn], (en >> TC_NSLOT_LOG2) & 1) ? 1 : 0, 0) != 0) {
-        const Meta& mn = meta[sn];
-        if (mn.ncand >= 0) {
-          tc_first_codes(P, dw, lane, mn.L, mn.nchunk, mn.n0, mn.n1, mn.e0, next_codes);
-          have_next = true;
-        }
-      }
-    }
     { TCP_BEGIN();
-    if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.nchunk, m.n0, m.n1, m.e0, ring + m.b_off, nullptr, have_first, first_codes);
+    if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.nchunk, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
     TCP_END(20); }
-    have_first = have_next;
-#pragma unroll
-    for (int i = 0; i < TC_DBATCH; i++) first_codes[i] = have_next ? next_codes[i] : 0;
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) { ptx::mbar_arrive(&bar->b_full[slot]); ptx::mbar_arrive(&bar->meta_empty[slot]); }
@@ -765,7 +706,7 @@ k_maxsim_tc(TcParams P) {
   if (tid == 0) {
     for (int i = 0; i < TC_NSLOT; i++) {
       ptx::mbar_init(&bar->b_full[i], TC_NDEC_WARPS / TC_NTEAMS); ptx::mbar_init(&bar->b_empty[i], TC_NISSUE);
-      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + ((TC_NISSUE == 2 && !(TC_NI_DBG & 1)) ? 2 : 0));
+      ptx::mbar_init(&bar->meta_full[i], 1);          ptx::mbar_init(&bar->meta_empty[i], TC_NLOAD + TC_NEPI_WARPS + TC_NDEC_WARPS + (TC_NISSUE == 2 ? 2 : 0));
     }
     for (int i = 0; i < TC_NACC_; i++) {
       for (int s = 0; s < TC_EPI_SETS; s++) ptx::mbar_init(&bar->d_full[s][i], 1);
@@ -1071,8 +1012,7 @@ k_tc_dump(TcParams P, const int32_t* __restrict__ pids, const int64_t* __restric
   int nchunk, n0, n1;
   tc_tile_geometry(L, nchunk, n0, n1);
   const uint8_t* lut_lane = s_lut + (lane & (LutGeom<NBITS>::REPLICAS - 1)) * LutGeom<NBITS>::ENTRY_BYTES;
-  const int32_t no_codes[TC_DBATCH] = {};
-  tc_decompress_passage<NBITS, true>(P, lut_lane, dw, lane, L, nchunk, n0, n1, e0, tile0, out_raw + out_off[blockIdx.x] * TC_DIM, false, no_codes);
+  tc_decompress_passage<NBITS, true>(P, lut_lane, dw, lane, L, nchunk, n0, n1, e0, tile0, out_raw + out_off[blockIdx.x] * TC_DIM);
   __syncthreads();
   // row rr of chunk c, 16-byte chunk j (K-block j >> 3): the inverse of the address finish_token16 wrote
   for (int i = tid; i < L * 16; i += 32 * TC_TEAM_WARPS) {
