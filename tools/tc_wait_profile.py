@@ -3,10 +3,9 @@ CB_TC_PROF_OUT is set): clocks per 4-query group, averaged over the CTAs.  Usage
 import sys
 import numpy as np
 
-TAGS2 = {4: "iss:meta_full", 5: "iss:b_full", 6: "iss:l_afull", 7: "iss:l_dempty", 10: "work:meta_full(epi)", 11: "work:l_dfull", 13: "work:meta_full(conv)", 14: "work:a_full(stage)", 16: "iss:issue(busy)"}
 TAGS = {1: "sched:meta_empty", 2: "sched:b_empty", 3: "sched:end", 4: "mma:meta_full", 5: "mma:b_full", 6: "mma:a_full", 7: "mma:d_empty",
-        8: "load:meta_full", 9: "load:a_empty", 10: "epi:meta_full", 11: "epi:d_full", 12: "dec:meta_full", 13: "conv:meta_full",
-        14: "conv:a_full", 15: "conv:at_empty", 16: "mma:issue(busy)", 18: "conv:group(incl at_empty)", 20: "dec:passage(busy)"}
+        8: "load:meta_full", 9: "load:a_empty", 10: "epi:meta_full", 11: "epi:d_full", 12: "dec:meta_full", 16: "mma:issue(busy)",
+        20: "dec:passage(busy)"}
 p = np.load(sys.argv[1]).astype(np.float64)          # [cta][warp][tag]
 groups = float(sys.argv[2]) if len(sys.argv) > 2 else None
 ncta = int((p[:, 0, 0] > 0).sum())
