@@ -41,6 +41,9 @@ namespace {
 #ifndef TC_EPI_SETS
 #define TC_EPI_SETS 2                  // epilogue warp sets (each set = 4 warps); with two issuers set s reads issuer s's accumulator(s)
 #endif
+#ifndef TC_L2_HINTS
+#define TC_L2_HINTS 2                  // 1 = query-tile bulk copies carry an L2 evict_last policy (no effect); 2 = packed codes / residuals, read once per batch, are loaded with ld.global.cs (evict first: ~1 % at C, profiles/r02_ab_two_issuer_tuning.txt); 3 = both
+#endif
 #ifndef TC_BACKOFF_NS
 #define TC_BACKOFF_NS 0                // nanosleep between polls of the waits that are usually long and have slack (loaders: free stage, scheduler: slot / ring)
 #endif
@@ -218,6 +221,12 @@ template <int NBITS> struct Bits16 { uint32_t lo, hi; };   // NBITS bytes each: 
 template <int NBITS>
 __device__ __forceinline__ Bits16<NBITS> load_bits16(const uint8_t* __restrict__ emb, int l8) {
   Bits16<NBITS> b;
+  if constexpr (TC_L2_HINTS & 2) {     // read once per batch: evict first
+    if constexpr (NBITS == 1) { b.lo = __ldcs(emb + l8); b.hi = __ldcs(emb + 8 + l8); }
+    else if constexpr (NBITS == 2) { b.lo = __ldcs(reinterpret_cast<const uint16_t*>(emb) + l8); b.hi = __ldcs(reinterpret_cast<const uint16_t*>(emb) + 8 + l8); }
+    else { b.lo = __ldcs(reinterpret_cast<const uint32_t*>(emb) + l8); b.hi = __ldcs(reinterpret_cast<const uint32_t*>(emb) + 8 + l8); }
+    return b;
+  }
   if constexpr (NBITS == 1) { b.lo = emb[l8]; b.hi = emb[8 + l8]; }
   else if constexpr (NBITS == 2) { b.lo = reinterpret_cast<const uint16_t*>(emb)[l8]; b.hi = reinterpret_cast<const uint16_t*>(emb)[8 + l8]; }
   else { b.lo = reinterpret_cast<const uint32_t*>(emb)[l8]; b.hi = reinterpret_cast<const uint32_t*>(emb)[8 + l8]; }
@@ -364,7 +373,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 #pragma unroll
   for (int i = 0; i < TC_DBATCH; i++) {
     const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
-    code_next[i] = (i < per && i < nround) ? P.codes[e0 + t] : 0;
+    code_next[i] = (i < per && i < nround) ? ((TC_L2_HINTS & 2) ? __ldcs(P.codes + e0 + t) : P.codes[e0 + t]) : 0;
   }
   for (int j0 = 0; j0 < nround; j0 += per) {
     Bits16<NBITS> bits[TC_DBATCH];
@@ -382,7 +391,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 #pragma unroll
     for (int i = 0; i < TC_DBATCH; i++) {
       const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + per + i), L - 1);
-      code_next[i] = (i < per && j0 + per + i < nround) ? P.codes[e0 + t] : 0;
+      code_next[i] = (i < per && j0 + per + i < nround) ? ((TC_L2_HINTS & 2) ? __ldcs(P.codes + e0 + t) : P.codes[e0 + t]) : 0;
     }
 #pragma unroll
     for (int i = 0; i < TC_DBATCH; i++) {
@@ -413,6 +422,7 @@ __device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S
   Barriers* const bar = S.bar; Meta* const meta = S.meta; uint8_t* const a_tile0 = S.a_tile0; const int NA = S.NA;
   (void)warp;
   uint32_t st = 0, a_par = 1;   // stage of the current group / parity of its next a_empty phase
+  [[maybe_unused]] const uint64_t l2pol = (TC_L2_HINTS & 1) ? ptx::l2_policy_evict_last() : 0ull;
   [[maybe_unused]] uint32_t turn = 0;   // TC_NISSUE == 2: issuer of the current group
   [[maybe_unused]] int gc = 0;
   for (int e = 0;; e++) {
@@ -448,8 +458,10 @@ __device__ __forceinline__ void tc_loader_role(const TcParams& P, const TcCtx& S
       if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full, (uint32_t)nmine * TC_Q_BYTES);
       for (int i = 0; i < nmine; i++) {
         const int q = __shfl_sync(0xffffffffu, qv, i);
-        if (ptx::elect_one())
-          ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full);
+        if (ptx::elect_one()) {
+          if (TC_L2_HINTS & 1) ptx::bulk_g2s_hint(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full, l2pol);
+          else ptx::bulk_g2s(dst + (li + i * NLOAD) * TC_Q_BYTES, P.qprep + (size_t)q * TC_Q_BYTES, TC_Q_BYTES, full);
+        }
       }
     }
     __syncwarp();
