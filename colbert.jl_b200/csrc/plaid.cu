@@ -166,6 +166,33 @@ k_plaid_approx(const int64_t* __restrict__ offsets, int64_t Np, const int32_t* _
     __syncwarp();
     int nh = s_n[wi];
     if (nh > PL_HCAP) { if (lane == 0) atomicExch(overflow, 1); nh = PL_HCAP; }
+    // Fast path (the usual case: ~12 hits per passage at C, almost all for different queries): one LANE per hit.  With no
+    // two hits for the same query there is nothing to maximise over, a hit's score is the sum of its own 32-float row, and the
+    // lane forms it in the association order of the xor-shuffle tree below (oracle.tree_sum32: x[t] + x[t ^ 16] first, then
+    // strides 8, 4, 2, 1 -- elementwise on the eight float4 of the row for the first three levels), so the bits are the same.
+    if (nh <= 32) {
+      const bool valid = lane < nh;
+      const uint32_t q = valid ? (uint32_t)s_hq[wi][lane] : 0u;
+      const bool dup = __match_any_sync(0xffffffffu, valid ? q : (0x10000u + (uint32_t)lane)) != (1u << lane);
+      if (!__any_sync(0xffffffffu, dup)) {
+        if (valid) {
+          const float4* __restrict__ row = reinterpret_cast<const float4*>(vec + (int64_t)s_hit[wi][lane] * 32);
+          auto add4 = [](const float4 a, const float4 b) {
+            return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+          };
+          const float4 ab = add4(add4(row[0], row[4]), add4(row[2], row[6]));     // t = 0..3: (x[t] + x[t+16]) + (x[t+8] + x[t+24])
+          const float4 cd = add4(add4(row[1], row[5]), add4(row[3], row[7]));     //           (x[t+4] + x[t+20]) + (x[t+12] + x[t+28])
+          const float4 s4 = add4(ab, cd);
+          const float m = __fadd_rn(__fadd_rn(s4.x, s4.z), __fadd_rn(s4.y, s4.w));
+          if (m > 0.f) {
+            const int pos = atomicAdd(&cursors[q], 1);
+            pairs[list_off[q] + pos] = ((uint64_t)cb_orderable(m) << 32) | (uint64_t)(0xffffffffu - (uint32_t)p);
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     // fold the hits query by query: hit i leads if no earlier hit has its query.  The positive scores
     // are parked in shared memory (slot k <= i of s_hit is dead by then) and appended afterwards with
     // all the atomics of the passage in flight at once, instead of one dependent round trip per hit.
