@@ -557,7 +557,7 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
   // ~17 candidates per passage: nothing downstream ever saw a full pipeline).
   struct Hdr { int64_t o0, o1, f0, f1, p; uint32_t w; };
   // With a passage list (sparse bitmap) item i is passage pid_list[i]: the pid is requested one more
-  // iteration ahead than the header that depends on it.  (No packed-byte prefetch in that mode.)
+  // iteration ahead than the header that depends on it.
   const int64_t n_items = P.pid_list ? P.n_list : P.Np;
   auto pid_of = [&](int64_t i) -> int64_t { return (P.pid_list && i < n_items) ? (int64_t)P.pid_list[i] : i; };
   auto load_hdr = [&](int64_t i, int64_t p) {
@@ -582,10 +582,13 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     const int64_t e0 = h.o0;
     const int L = (int)(h.o1 - h.o0);
     uint32_t w = h.w;
-    if (h.f1 > h.f0 && !(TC_ABLATE & 32)) {
-      const char* r0 = reinterpret_cast<const char*>(P.residuals) + h.f0 * P.R;
-      const char* c0 = reinterpret_cast<const char*>(P.codes) + h.f0 * 4;
-      const int64_t rbytes = (h.f1 - h.f0) * P.R, cbytes = (h.f1 - h.f0) * 4;
+    // packed bytes to pull from HBM into L2 ahead of the decompression teams: the passage 6 steps ahead (whole index), or -- with a
+    // passage list, where a passage is only known one header ahead -- the NEXT item (its header was requested an iteration ago)
+    const int64_t pf0 = P.pid_list ? h1.o0 : h.f0, pf1 = P.pid_list ? h1.o1 : h.f1;
+    if (pf1 > pf0 && !(TC_ABLATE & 32)) {
+      const char* r0 = reinterpret_cast<const char*>(P.residuals) + pf0 * P.R;
+      const char* c0 = reinterpret_cast<const char*>(P.codes) + pf0 * 4;
+      const int64_t rbytes = (pf1 - pf0) * P.R, cbytes = (pf1 - pf0) * 4;
       for (int64_t o = (int64_t)lane * 128; o < rbytes; o += 32 * 128) ptx::prefetch_l2(r0 + o);
       for (int64_t o = (int64_t)lane * 128; o < cbytes; o += 32 * 128) ptx::prefetch_l2(c0 + o);
     }
