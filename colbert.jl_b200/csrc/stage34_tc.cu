@@ -41,6 +41,9 @@ namespace {
 #ifndef TC_EPI_SETS
 #define TC_EPI_SETS 2                  // epilogue warp sets (each set = 4 warps); with two issuers set s reads issuer s's accumulator(s)
 #endif
+#ifndef TC_META_CODES
+#define TC_META_CODES 128              // centroid codes of a passage's first tokens staged in its meta slot by the scheduler (0 = the decompression teams load all codes themselves)
+#endif
 #ifndef TC_L2_HINTS
 #define TC_L2_HINTS 2                  // 1 = query-tile bulk copies carry an L2 evict_last policy (no effect); 2 = packed codes / residuals, read once per batch, are loaded with ld.global.cs (evict first: ~1 % at C, profiles/r02_ab_two_issuer_tuning.txt); 3 = both
 #endif
@@ -169,6 +172,7 @@ struct Meta {            // one passage entry, written by the scheduler
   uint32_t pad_;
   long long e0;          // first embedding of the passage
   uint16_t q[CB_NQ_CHUNK];
+  int32_t codes[TC_META_CODES > 0 ? TC_META_CODES : 1];   // codes of tokens 0 .. TC_META_CODES-1 (see tc_scheduler_role)
 };
 
 struct Barriers {
@@ -359,8 +363,14 @@ constexpr int TC_TEAM_WARPS = TC_NDEC_WARPS / TC_NTEAMS;
 // decompression role and, unchanged, by the parity hook kernel k_tc_dump (DUMP = true).
 template <int NBITS, bool DUMP>
 __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const uint8_t* __restrict__ lut_lane, int dw, int lane,
-                                                      int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out) {
+                                                      int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out,
+                                                      const int32_t* s_codes = nullptr) {
   constexpr int TEAM_WARPS = TC_TEAM_WARPS;
+  // code of token t: from the meta slot (staged by the scheduler) when it is there, else from global memory
+  auto code_of = [&](int t) -> int32_t {
+    if (TC_META_CODES > 0 && s_codes != nullptr && t < TC_META_CODES) return s_codes[t];
+    return (TC_L2_HINTS & 2) ? __ldcs(P.codes + e0 + t) : P.codes[e0 + t];
+  };
   const int l8 = lane & 7;
   const int nrows = tc_total_rows(nchunk, n0, n1);              // operand rows (multiple of 16)
   // operand row of this lane in round j: rr = 4 * (dw + TEAM_WARPS * j) + (lane >> 3)
@@ -373,7 +383,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 #pragma unroll
   for (int i = 0; i < TC_DBATCH; i++) {
     const int t = min(rr0 + 4 * TEAM_WARPS * i, L - 1);
-    code_next[i] = (i < per && i < nround) ? ((TC_L2_HINTS & 2) ? __ldcs(P.codes + e0 + t) : P.codes[e0 + t]) : 0;
+    code_next[i] = (i < per && i < nround) ? code_of(t) : 0;
   }
   for (int j0 = 0; j0 < nround; j0 += per) {
     Bits16<NBITS> bits[TC_DBATCH];
@@ -391,7 +401,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
 #pragma unroll
     for (int i = 0; i < TC_DBATCH; i++) {
       const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + per + i), L - 1);
-      code_next[i] = (i < per && j0 + per + i < nround) ? ((TC_L2_HINTS & 2) ? __ldcs(P.codes + e0 + t) : P.codes[e0 + t]) : 0;
+      code_next[i] = (i < per && j0 + per + i < nround) ? code_of(t) : 0;
     }
 #pragma unroll
     for (int i = 0; i < TC_DBATCH; i++) {
@@ -572,9 +582,28 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
   };
   Hdr h1 = load_hdr(first, pid_of(first)), h2 = load_hdr(first + stride, pid_of(first + stride));
   int64_t pq = pid_of(first + 2 * stride);
+  // The centroid codes of a passage's first TC_META_CODES tokens ride along in its meta slot: code -> centroid row is a dependent
+  // pair of global round trips for the decompression teams (~1.5k clocks each under load, two to three times per passage);
+  // the scheduler requests the codes of the NEXT item one iteration ahead, so the teams start at the second round trip.
+  constexpr int NCR = (TC_META_CODES + 31) / 32;
+  [[maybe_unused]] int32_t c_next[NCR > 0 ? NCR : 1];
+  auto load_codes = [&](const Hdr& hh, int32_t (&c)[NCR > 0 ? NCR : 1]) {
+#pragma unroll
+    for (int j = 0; j < NCR; j++) {
+      const int64_t t = lane + 32 * j;
+      c[j] = (t < hh.o1 - hh.o0) ? P.codes[hh.o0 + t] : 0;
+    }
+  };
+  if (TC_META_CODES > 0) load_codes(h1, c_next);
   for (int64_t it = first; it < n_items; it += stride) {
     const Hdr h = h1;
     h1 = h2;
+    [[maybe_unused]] int32_t c_cur[NCR > 0 ? NCR : 1];
+    if (TC_META_CODES > 0) {
+#pragma unroll
+      for (int j = 0; j < NCR; j++) c_cur[j] = c_next[j];
+      load_codes(h1, c_next);
+    }
     const int64_t pq_next = pid_of(it + 3 * stride);
     h2 = load_hdr(it + 2 * stride, pq);
     pq = pq_next;
@@ -633,6 +662,10 @@ __device__ __forceinline__ void tc_scheduler_role(const TcParams& P, const TcCtx
     int base = pre - c;
     while (w) { const int b = __ffs(w) - 1; w &= w - 1; m.q[base++] = (uint16_t)(lane * 32 + b); }
     const int ncand = __shfl_sync(0xffffffffu, pre, 31);
+    if (TC_META_CODES > 0) {
+#pragma unroll
+      for (int j = 0; j < NCR; j++) m.codes[lane + 32 * j] = c_cur[j];
+    }
     if (lane == 0) {
       m.ncand = ncand; m.L = L; m.nchunk = nchunk; m.n0 = n0; m.n1 = n1; m.pid = (int)p; m.b_off = off; m.e0 = e0;
     }
@@ -683,7 +716,7 @@ __device__ __forceinline__ void tc_decompress_role(const TcParams& P, const TcCt
     const Meta& m = meta[slot];
     if (dw == 0) TCE(9, e);
     { TCP_BEGIN();
-    if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.nchunk, m.n0, m.n1, m.e0, ring + m.b_off, nullptr);
+    if (!(TC_ABLATE & 4)) tc_decompress_passage<NBITS, false>(P, lut_lane, dw, lane, m.L, m.nchunk, m.n0, m.n1, m.e0, ring + m.b_off, nullptr, m.codes);
     TCP_END(20); }
     ptx::fence_proxy_async();
     __syncwarp();
