@@ -109,6 +109,13 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
                : "memory");
 }
 
+// 16-byte global load with an L2 cache policy
+__device__ __forceinline__ uint4 ld_global_v4_hint(const void* p, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+  return v;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- tcgen05 ---------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ namespace {
 #define TC_META_CODES 128              // centroid codes of a passage's first tokens staged in its meta slot by the scheduler (0 = the decompression teams load all codes themselves)
 #endif
 #ifndef TC_L2_HINTS
-#define TC_L2_HINTS 2                  // 1 = query-tile bulk copies carry an L2 evict_last policy (no effect); 2 = packed codes / residuals, read once per batch, are loaded with ld.global.cs (evict first: ~1 % at C, profiles/r02_ab_two_issuer_tuning.txt); 3 = both
+#define TC_L2_HINTS 2                  // 1 = query-tile bulk copies carry an L2 evict_last policy (no effect); 2 = packed codes / residuals, read once per batch, are loaded with ld.global.cs (evict first: ~1 % at C, profiles/r02_ab_two_issuer_tuning.txt); 4 = the fp16 centroid rows are loaded with an L2 evict_last policy
 #endif
 #ifndef TC_BACKOFF_NS
 #define TC_BACKOFF_NS 0                // nanosleep between polls of the waits that are usually long and have slack (loaders: free stage, scheduler: slot / ring)
@@ -366,6 +366,7 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
                                                       int L, int nchunk, int n0, int n1, int64_t e0, uint8_t* tile0, __half* raw_out,
                                                       const int32_t* s_codes = nullptr) {
   constexpr int TEAM_WARPS = TC_TEAM_WARPS;
+  [[maybe_unused]] const uint64_t l2_keep = (TC_L2_HINTS & 4) ? ptx::l2_policy_evict_last() : 0ull;   // centroid rows: re-read ~2300 times per batch
   // code of token t: from the meta slot (staged by the scheduler) when it is there, else from global memory
   auto code_of = [&](int t) -> int32_t {
     if (TC_META_CODES > 0 && s_codes != nullptr && t < TC_META_CODES) return s_codes[t];
@@ -394,8 +395,8 @@ __device__ __forceinline__ void tc_decompress_passage(const TcParams& P, const u
         const int t = min(rr0 + 4 * TEAM_WARPS * (j0 + i), L - 1);
         bits[i] = load_bits16<NBITS>(P.residuals + (e0 + t) * P.R, l8);
         const uint4* crow = reinterpret_cast<const uint4*>(P.centroids_h + (int64_t)code_next[i] * TC_DIM) + l8;
-        cr[i][0] = crow[0];
-        cr[i][1] = crow[8];
+        if (TC_L2_HINTS & 4) { cr[i][0] = ptx::ld_global_v4_hint(crow, l2_keep); cr[i][1] = ptx::ld_global_v4_hint(crow + 8, l2_keep); }
+        else { cr[i][0] = crow[0]; cr[i][1] = crow[8]; }
       }
     }
 #pragma unroll
