@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("COLBERT_B200_LIB") or os.path.join(_HERE, "lib", "lib
 
 CB_OK, CB_ERR_BAD_ARG, CB_ERR_DOMAIN, CB_ERR_CUDA, CB_ERR_OOM, CB_ERR_UNSUPPORTED, CB_ERR_BOUNDS = range(7)
 CB_FLAG_DEVICE_POINTERS = 1
+CB_FLAG_BORROW_RESIDUALS = 2
 
 # name -> (restype, argtypes); exactly the symbols include/colbert_b200.h declares
 _p = C.c_void_p

@@ -109,6 +109,7 @@ struct cb_index {
   float* weights = nullptr;          // [2^nbits]
   int32_t* codes = nullptr;          // [Ne] 0-based
   uint8_t* residuals = nullptr;      // [Ne][R]
+  bool residuals_borrowed = false;   // CB_FLAG_BORROW_RESIDUALS: the caller's array, not freed here
   int64_t* offsets = nullptr;        // [Np+1] exclusive prefix sum of doclens
   int64_t* cell_offsets = nullptr;   // [K+1]  exclusive prefix sum of ivf_lengths
   int32_t* ivf_pids = nullptr;       // [Ne]   local 0-based pid of every IVF entry

@@ -170,7 +170,8 @@ static void destroy_index(cb_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
   cudaFree(ix->centroids); cudaFree(ix->centroids_h); cudaFree(ix->centroids_img); cudaFree(ix->weights); cudaFree(ix->codes);
-  cudaFree(ix->residuals); cudaFree(ix->offsets); cudaFree(ix->cell_offsets); cudaFree(ix->ivf_pids);
+  if (!ix->residuals_borrowed) cudaFree(ix->residuals);
+  cudaFree(ix->offsets); cudaFree(ix->cell_offsets); cudaFree(ix->ivf_pids);
   DevBuf* bufs[] = {&ix->q_f32, &ix->q_prep, &ix->topr_val, &ix->topr_idx, &ix->cells, &ix->cell_scores,
                     &ix->flags, &ix->bitmap, &ix->counts, &ix->list_off, &ix->cursors, &ix->pairs,
                     &ix->out_pids, &ix->out_scores, &ix->out_counts, &ix->misc, &ix->long_list,
@@ -238,9 +239,14 @@ static int32_t create_impl(cb_index* ix, const float* centroids, const float* bu
 
   // compressed embeddings
   CB_DEVALLOC(ix->codes, sizeof(int32_t) * Ne);
-  CB_DEVALLOC(ix->residuals, (size_t)Ne * ix->R);
   CB_TRY(upload(ix->codes, codes, sizeof(uint32_t) * Ne, flags));
-  CB_TRY(upload(ix->residuals, residuals, (size_t)Ne * ix->R, flags));
+  if ((flags & CB_FLAG_DEVICE_POINTERS) && (flags & CB_FLAG_BORROW_RESIDUALS)) {
+    ix->residuals = const_cast<uint8_t*>(residuals);     // read in place: the layout is the reference's Matrix{UInt8}(R, Ne) as is
+    ix->residuals_borrowed = true;
+  } else {
+    CB_DEVALLOC(ix->residuals, (size_t)Ne * ix->R);
+    CB_TRY(upload(ix->residuals, residuals, (size_t)Ne * ix->R, flags));
+  }
   k_codes_zero_based<<<grid_for(Ne), 256>>>(ix->codes, Ne, K, d_bad);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemcpy(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));

@@ -92,9 +92,11 @@ class Searcher:
 
     @classmethod
     def from_device(cls, config: ColBERTConfig, K, n_passages, n_embeddings, centroids_ptr, bucket_weights_ptr,
-                    codes_ptr, residuals_ptr, doclens_ptr, ivf_ptr=None, ivf_lengths_ptr=None, device=0, pid_base=0):
+                    codes_ptr, residuals_ptr, doclens_ptr, ivf_ptr=None, ivf_lengths_ptr=None, device=0, pid_base=0,
+                    borrow_residuals=False):
         """Index whose arrays already live in device memory (raw device pointers, C layouts of the
-        header): the hand-off a device-side loader / generator uses."""
+        header): the hand-off a device-side loader / generator uses.  `borrow_residuals`: the index reads the
+        caller's residual array in place (no second copy of the bulk of the index); the caller keeps it alive until close()."""
         lib = L.load()
         self = cls.__new__(cls)
         self.config, self.device, self.pid_base = config, device, int(pid_base)
@@ -103,7 +105,8 @@ class Searcher:
         self._h = C.c_void_p()
         L.check(lib.cb_index_create(C.byref(self._h), device, config.dim, config.nbits, self.K, self.n_passages,
                                     self.n_embeddings, centroids_ptr, bucket_weights_ptr, codes_ptr, residuals_ptr,
-                                    doclens_ptr, ivf_ptr, ivf_lengths_ptr, self.pid_base, L.CB_FLAG_DEVICE_POINTERS))
+                                    doclens_ptr, ivf_ptr, ivf_lengths_ptr, self.pid_base,
+                                    L.CB_FLAG_DEVICE_POINTERS | (L.CB_FLAG_BORROW_RESIDUALS if borrow_residuals else 0)))
         return self
 
     @classmethod

@@ -44,6 +44,9 @@ extern "C" {
 
 /* flags for cb_index_create */
 #define CB_FLAG_DEVICE_POINTERS 1 /* all array arguments are device pointers on `device` */
+#define CB_FLAG_BORROW_RESIDUALS 2 /* with CB_FLAG_DEVICE_POINTERS: the index reads the caller's `residuals` array in place instead of
+                                      copying it (the bulk of an index: 19 GB at 8.8 M passages); the caller keeps it alive and
+                                      unmodified until cb_index_destroy, which does not free it */
 
 typedef struct cb_index cb_index; /* opaque: one index shard resident in the HBM of one GPU */
 typedef struct cb_multi cb_multi; /* opaque: the passage-range shards of one index on several GPUs of one box */

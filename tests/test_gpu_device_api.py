@@ -72,6 +72,15 @@ def test_index_from_device_pointers(small):
     finally:
         s.close()
     assert np.array_equal(hp, dp) and np.array_equal(hs, ds) and np.array_equal(hc, dc)
+    # CB_FLAG_BORROW_RESIDUALS: the caller's residual array is read in place (and survives the index)
+    s = cb.Searcher.from_device(cfg, cen.shape[0], dl.numel(), codes.numel(), cen.data_ptr(), w.data_ptr(), codes.data_ptr(),
+                                res.data_ptr(), dl.data_ptr(), None, None, device=0, borrow_residuals=True)
+    try:
+        bp, bs, bc = _device_search(s, Q, 7)
+    finally:
+        s.close()
+    assert np.array_equal(hp, bp) and np.array_equal(hs, bs) and np.array_equal(hc, bc)
+    assert torch.equal(res.cpu(), torch.from_numpy(ix["residuals"]))      # untouched and still allocated
 
 
 def test_more_queries_than_one_chunk(small):
