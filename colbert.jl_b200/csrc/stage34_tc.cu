@@ -79,8 +79,8 @@ constexpr int TC_NEPI_WARPS = 4 * TC_EPI_SETS;
 constexpr int TC_DEC_WARP0 = 4 + TC_NEPI_WARPS;   // first warp after the epilogue sets
 constexpr int TC_DIM = 128, TC_T = 32;
 #ifndef TC_NACC
-#define TC_NACC 2                      // TMEM accumulators (shared-memory A operand): 2 x 256 columns, or 4 x 128 so that the MMA issuer can run
-#endif                                 // three groups ahead of the epilogue (passages over 128 tokens then take up to 4 chunks)
+#define TC_NACC 2                      // TMEM accumulators: 2 x 256 columns (one per issuer), or 4 x 128 (two per issuer; passages over 128 tokens
+#endif                                 // then take up to 4 chunks: measured no faster at C and slower at B)
 constexpr int TC_MAX_BROWS = (TC_NACC == 4) ? 128 : 240;   // rows (tokens) per chunk; multiple of 16, <= accumulator columns
 constexpr int TC_MAX_CHUNKS = (TC_NACC == 4) ? 4 : 2; // chunks per passage (accumulator passes per group)
 constexpr int TC_MAX_ASTAGES = 6;
@@ -114,7 +114,6 @@ template <int N> __device__ __forceinline__ void tc_reg_budget() {   // a role's
   else if constexpr (N > 0 && N < TC_LAUNCH_REGS) ptx::reg_dec<N>();
 }
 // tensor memory: TC_NACC accumulators of TC_D_COLS fp32 columns
-// (128 lanes x 128 fp16 = 64 packed 32-bit columns: lane = (query, token) row, column j = dims 2j, 2j+1)
 constexpr int TC_NACC_ = TC_NACC;
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D_COLS = 512 / TC_NACC_;
 
